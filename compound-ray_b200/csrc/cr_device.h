@@ -1,0 +1,113 @@
+// cr_device.h -- device-side data layout shared by the builder, the kernels and the renderer.
+//
+// HBM layout (all buffers 256-byte aligned by cudaMalloc):
+//   nodes   float4[4*nNodes]   64 B per BVH2 node, both child boxes inline:
+//             n[0] = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
+//             n[1] = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
+//             n[2] = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
+//             n[3] = (ref0, ref1, unused, unused) as int bits
+//           child ref >= 0 : internal node index;  ref < 0 : leaf,  x = ~ref,
+//           first triangle = x >> 3 (position in the sorted array), count = (x & 7) + 1
+//   tris    float4[3*nTris]    48 B per triangle in BVH (Morton) order:
+//             t[0] = (v0.xyz, flattened primitive index as int bits)
+//             t[1] = (e1.xyz = v1 - v0, 0)     t[2] = (e2.xyz = v2 - v0, 0)
+//   prims   uint4[nTris]       per flattened primitive: global vertex ids i0,i1,i2 and mesh group
+//   uvs     float2[nVerts]     colors float4[nVerts]   (only when some mesh has them)
+//   meshes  MeshRec[nMeshes]
+// Compound eye (per camera):
+//   omm     float4[2*N]        the 32-byte ommatidium rows as loaded
+//   rng     uint4[2*N*S]       32 B compact XORWOW state per sample stream, laid out [o][s]
+//             r[0] = (d, v0, v1, v2)   r[1] = (v3, v4, boxmuller_flag, boxmuller_extra bits)
+//   summed  float4[N]          per-ommatidium RGB (sum over samples of colour/S)
+//   samples float[3*S*N]       optional, reference layout [N*s+o] (raw_ommatidial_samples only)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace cr {
+
+struct MeshRec {
+    int colorType;      // -1 none
+    int hasUV;
+    int hasTex;
+    int pad;
+    unsigned long long tex;   // cudaTextureObject_t
+    float baseColor[4];
+};
+
+struct DeviceScene {
+    const float4* nodes = nullptr;
+    const float4* tris = nullptr;
+    const uint4* prims = nullptr;
+    const float2* uvs = nullptr;
+    const float4* colors = nullptr;
+    const MeshRec* meshes = nullptr;
+    int nNodes = 0;
+    int nTris = 0;
+    int missShader = 0;
+};
+
+struct DevicePose {
+    float px, py, pz;
+    float xx, xy, xz;
+    float yx, yy, yz;
+    float zx, zy, zz;
+};
+
+struct EyeParams {
+    const float4* omm = nullptr;
+    uint4* rng = nullptr;
+    float4* summed = nullptr;
+    float* samples = nullptr;
+    // optional per-ray dump (debug / parity): reference stream-id order [N*s+o]
+    float* dumpOrigins = nullptr;
+    float* dumpDirs = nullptr;
+    int4* dumpHits = nullptr;     // (prim, t bits, u bits, v bits)
+    int N = 0;
+    int S = 0;
+    int tileOmm = 1;              // ommatidia per CTA tile
+    int chunk = 1;                // samples per chunk (<= kTileRays)
+    int nTiles = 0;
+    DevicePose pose;
+};
+
+constexpr int kTraceThreads = 128;
+constexpr int kTileRays = 512;
+constexpr float kTMax = 1e16f;
+
+struct BvhBuildResult {
+    float4* nodes = nullptr;
+    float4* tris = nullptr;
+    int nNodes = 0;
+    int nTris = 0;
+    double buildMs = 0.0;
+};
+
+// Builds the LBVH on `stream` from world-space positions + indices already on the device.
+// sceneMin/sceneMax bound all vertices.  leafSize in [1,8].
+BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int nTris, const float sceneMin[3],
+                         const float sceneMax[3], int leafSize, cudaStream_t stream);
+
+// projection modes (suffix after "__raygen__compound_projection_", libEyeRenderer3/shaders.cu:354-640)
+enum Projection : int {
+    PROJ_RAW_SAMPLES = 0, PROJ_SINGLE_DIM = 1, PROJ_SINGLE_DIM_FAST = 2, PROJ_SPH_POSITIONWISE = 3,
+    PROJ_SPH_ORIENTATIONWISE = 4, PROJ_SPH_SPLIT_ORIENTATIONWISE = 5, PROJ_SPH_ORIENTATIONWISE_IDS = 6,
+    PROJ_SPH_POSITIONWISE_IDS = 7, PROJ_UNKNOWN = -1
+};
+
+// kernel launchers (cr_kernels.cu)
+void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cudaStream_t stream);
+void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);
+void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream);
+void launchProjectMap(bool ids, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchPackRow(const float4* summed, int N, uchar4* out, cudaStream_t stream);
+void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame,
+                  int W, int H, cudaStream_t stream);
+void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,
+                     cudaStream_t stream);
+void launchEvalMath(int fn, const float* a, const float* b, float* out, int n, cudaStream_t stream);
+int traceKernelOccupancy();   // resident CTAs per SM for the compound trace kernel
+
+}  // namespace cr

@@ -1,0 +1,671 @@
+// cr_kernels.cu -- hand-written sm_100a kernels of the compound-eye render path.
+//
+// Replaces every live OptiX program of libEyeRenderer3/shaders.cu (reference lines cited at each
+// function).  Compile with -fmad=false and without --use_fast_math: the arithmetic below is
+// written one IEEE rounding per operation with explicit fmaf() where fusion is wanted, so the CPU
+// checker reproduces rays, hits and pixel maps bit for bit (see cr_math.h).
+//
+// K0  k_rngInit            curand_init(42, id, 0) per sample stream   (shaders.cu:680-685)
+// K1  k_traceCompound      raygen + BVH traversal + shading + exact-order per-ommatidium sum
+//                          (shaders.cu:664-731 + 110-137 + 740-811 + 341-347)
+// K2  k_projectVector/Raw  single_dimension[_fast], raw_ommatidial_samples (shaders.cu:354-406)
+// K3  k_buildProjectionMap nearest-ommatidium map of the spherical modes, cached per eye/size
+//     k_projectMap         map lookup + make_color, or ids                (shaders.cu:412-640)
+// K4  k_camera             pinhole / panoramic / orthographic primary rays (shaders.cu:198-333)
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+
+#include <cstdint>
+
+#include "cr_device.h"
+#include "cr_math.h"
+
+namespace cr {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// small vector helpers; plain versions follow sutil/vec_math.h (products then sums, left to right)
+// ------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vmuls(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float vdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b)
+{ return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float vlen(V3 a) { return sqrtf(vdot(a, a)); }
+__device__ __forceinline__ V3 vnormalize(V3 v) { const float inv = 1.0f / sqrtf(vdot(v, v)); return vmuls(v, inv); }
+// fused versions used by the intersection test (this renderer's own arithmetic; OptiX's is closed)
+__device__ __forceinline__ float fdot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ V3 fcross(V3 a, V3 b)
+{ return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))); }
+
+// ------------------------------------------------------------------------------------------
+// cuRAND XORWOW on a 32-byte compact state (curand_kernel.h:150-156, :863-874;
+// curand_normal.h:70-87,313-326; curand_uniform.h:69-72).  Streams/seeds as in shaders.cu:680-695.
+// ------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t d, v0, v1, v2, v3, v4;
+    int flag;
+    float extra;
+};
+__device__ __forceinline__ Rng rngLoad(const uint4* __restrict__ p)
+{
+    const uint4 a = p[0], b = p[1];
+    Rng r;
+    r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
+    r.flag = (int)b.z; r.extra = __uint_as_float(b.w);
+    return r;
+}
+__device__ __forceinline__ void rngStore(uint4* __restrict__ p, const Rng& r)
+{
+    p[0] = make_uint4(r.d, r.v0, r.v1, r.v2);
+    p[1] = make_uint4(r.v3, r.v4, (uint32_t)r.flag, __float_as_uint(r.extra));
+}
+__device__ __forceinline__ uint32_t rngNext(Rng& r)
+{
+    const uint32_t t = r.v0 ^ (r.v0 >> 2);
+    r.v0 = r.v1; r.v1 = r.v2; r.v2 = r.v3; r.v3 = r.v4;
+    r.v4 = (r.v4 ^ (r.v4 << 4)) ^ (t ^ (t << 1));
+    r.d += 362437u;
+    return r.v4 + r.d;
+}
+__device__ __forceinline__ float rngUniform(Rng& r)
+{
+    const uint32_t x = rngNext(r);
+    return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+__device__ __forceinline__ float rngNormal(Rng& r)
+{
+    if (r.flag != 1) {
+        const uint32_t x = rngNext(r);
+        const uint32_t y = rngNext(r);
+        const float u = (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+        const float v = (float)y * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2.0f);
+        const float s = sqrtf(-2.0f * crm::log(u));
+        float sn, cs;
+        crm::sincos(v, sn, cs);
+        r.extra = cs * s;
+        r.flag = 1;
+        return sn * s;
+    }
+    r.flag = 0;
+    return r.extra;
+}
+
+// K0: one thread per stream.  Stream id = N*s + o (shaders.cu:668-669); stored at [o*S + s].
+// firstFrame > 0 positions the stream as if `firstFrame` frames had already been rendered
+// (pose sharding / restart): skipahead(2*floor(k/2)*... ) raw draws, plus one replayed frame when
+// k is odd so that the Box-Muller cache is populated exactly as in the sequential run.
+__global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long long firstFrame)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * S) return;
+    const int o = (int)(i / S), s = (int)(i - (long long)o * S);
+    const unsigned long long id = (unsigned long long)N * (unsigned long long)s + (unsigned long long)o;
+    curandStateXORWOW_t st;
+    curand_init(42ull, id, 0ull, &st);
+    const unsigned long long evenFrames = firstFrame & ~1ull;
+    if (evenFrames) skipahead(2ull * evenFrames, &st);      // 3 + 1 draws per frame pair
+    Rng r;
+    r.d = st.d; r.v0 = st.v[0]; r.v1 = st.v[1]; r.v2 = st.v[2]; r.v3 = st.v[3]; r.v4 = st.v[4];
+    r.flag = 0; r.extra = 0.0f;
+    if (firstFrame & 1ull) { (void)rngNormal(r); (void)rngUniform(r); }
+    rngStore(rng + 2 * i, r);
+}
+
+// ------------------------------------------------------------------------------------------
+// Ommatidial sample ray (shaders.cu:648-662 generateOffsetRay/rotatePoint, :676-709)
+// ------------------------------------------------------------------------------------------
+#define CR_FWHM_SD_RATIO 2.35482004503094938202313865291f   /* shaders.cu:53 */
+
+__device__ __forceinline__ V3 rotatePoint(V3 p, float angle, V3 axis)   // axis NOT re-normalised
+{
+    float sn, cs;
+    crm::sincos(angle, sn, cs);
+    const V3 a = vmuls(p, cs);
+    const V3 b = vmuls(vcross(axis, p), sn);
+    const V3 c = vmuls(axis, (1.0f - cs) * vdot(axis, p));
+    return vadd(vadd(a, b), c);
+}
+__device__ __forceinline__ V3 generateOffsetRay(float axisAngle, float splay, V3 axis)
+{
+    V3 perp = vcross(mk(0.0f, 1.0f, 0.0f), axis);
+    if (perp.x + perp.y + perp.z == 0.0f) perp = mk(0.0f, 0.0f, 1.0f);   // exact-zero test on the SUM (:656)
+    else perp = vnormalize(perp);
+    const V3 splayed = rotatePoint(axis, splay, perp);
+    return rotatePoint(splayed, axisAngle, axis);
+}
+
+struct Ray { V3 o, d; float tmin; };
+
+__device__ __forceinline__ Ray ommatidialRay(const float4 q0, const float4 q1, const DevicePose& P, Rng& rng)
+{
+    const V3 relPos = mk(q0.x, q0.y, q0.z);
+    const V3 axis = mk(q0.w, q1.x, q1.y);
+    const float acceptance = q1.z, focal = q1.w;
+    const float sd = acceptance / CR_FWHM_SD_RATIO;
+    const float splay = rngNormal(rng) * sd;
+    const float axisAngle = rngUniform(rng) * crm::kPi;
+    const V3 rd = generateOffsetRay(axisAngle, splay, axis);
+    const V3 rp = vsub(relPos, vmuls(vnormalize(axis), focal));
+    const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
+    Ray r;
+    r.o = vadd(vadd(vadd(mk(P.px, P.py, P.pz), vmuls(X, rp.x)), vmuls(Y, rp.y)), vmuls(Z, rp.z));
+    r.d = vadd(vadd(vmuls(X, rd.x), vmuls(Y, rd.y)), vmuls(Z, rd.z));
+    r.tmin = focal;                                                   // shaders.cu:721
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit (stands in for optixTrace, shaders.cu:110-137): two-sided, closest t in
+// (tmin, tmax], ties on t resolved to the LOWEST flattened primitive index so the result does not
+// depend on traversal order.
+//
+// Box test: t = b*inv - o*inv as ONE fma per plane.  Conservative by construction:
+//   invN = inv*(1-2^-21), invF = inv*(1+2^-21)  absorb the rounding of 1/d and of the fma (both
+//          relative to |t|) for planes in front of the origin;
+//   addN = -(o*invN) - E, addF = -(o*invF) + E with E = 2^-21*|o*inv| absorb the rounding of the
+//          o*inv product (which is NOT relative to t).
+// Leaf boxes are additionally padded at build time (cr_bvh.cu) for the inexactness of the
+// triangle test itself, so BVH traversal returns exactly what a brute-force loop returns.
+// ------------------------------------------------------------------------------------------
+struct Hit { float t; int prim; float u, v; };
+
+struct RayBox {
+    float nix, niy, niz;      // invN
+    float fix, fiy, fiz;      // invF
+    float nax, nay, naz;      // addN
+    float fax, fay, faz;      // addF
+    bool sx, sy, sz;          // direction negative -> near plane is max
+};
+
+__device__ __forceinline__ void setupAxis(float o, float d, float& invN, float& invF, float& addN, float& addF, bool& neg)
+{
+    const float dc = (fabsf(d) < 1e-18f) ? copysignf(1e-18f, d) : d;
+    const float inv = 1.0f / dc;
+    neg = inv < 0.0f;
+    invN = inv * (1.0f - 4.76837158203125e-07f);
+    invF = inv * (1.0f + 4.76837158203125e-07f);
+    const float oN = o * invN, oF = o * invF;
+    const float E = fmaxf(fabsf(oN), fabsf(oF)) * 4.76837158203125e-07f;
+    addN = -oN - E;
+    addF = -oF + E;
+}
+
+__device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3 o, const V3 d, const float tmin,
+                                        const float tlimit, float& t, float& u, float& v, int& prim)
+{
+    const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+    const V3 v0 = mk(a.x, a.y, a.z), e1 = mk(b.x, b.y, b.z), e2 = mk(c.x, c.y, c.z);
+    const V3 p = fcross(d, e2);
+    const float det = fdot(e1, p);
+    if (!(det != 0.0f)) return false;
+    const float inv = 1.0f / det;
+    const V3 s = vsub(o, v0);
+    const float uu = fdot(s, p) * inv;
+    if (!(uu >= 0.0f && uu <= 1.0f)) return false;
+    const V3 q = fcross(s, e1);
+    const float vv = fdot(d, q) * inv;
+    if (!(vv >= 0.0f && uu + vv <= 1.0f)) return false;
+    const float tt = fdot(e2, q) * inv;
+    if (!(tt > tmin && tt <= tlimit)) return false;
+    t = tt; u = uu; v = vv; prim = __float_as_int(a.w);
+    return true;
+}
+
+constexpr int kStackDepth = 96;
+constexpr int kSentinel = (int)0x80000000;
+
+template <bool COUNT>
+__device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray& ray,
+                                            const float tmax, int* nodeCount, int* triCount)
+{
+    RayBox rb;
+    setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, rb.sx);
+    setupAxis(ray.o.y, ray.d.y, rb.niy, rb.fiy, rb.nay, rb.fay, rb.sy);
+    setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, rb.sz);
+    Hit best;
+    best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+    int stack[kStackDepth];
+    int sp = 0;
+    int cur = 0;
+    int nc = 0, tc = 0;
+    for (;;) {
+        while (cur >= 0) {
+            const float4 n0 = __ldg(nodes + 4 * (size_t)cur);
+            const float4 n1 = __ldg(nodes + 4 * (size_t)cur + 1);
+            const float4 n2 = __ldg(nodes + 4 * (size_t)cur + 2);
+            const float4 n3 = __ldg(nodes + 4 * (size_t)cur + 3);
+            if (COUNT) nc++;
+            // child 0
+            float tn0 = fmaf(rb.sx ? n0.y : n0.x, rb.nix, rb.nax);
+            tn0 = fmaxf(tn0, fmaf(rb.sy ? n0.w : n0.z, rb.niy, rb.nay));
+            tn0 = fmaxf(tn0, fmaf(rb.sz ? n2.y : n2.x, rb.niz, rb.naz));
+            tn0 = fmaxf(tn0, ray.tmin);
+            float tf0 = fmaf(rb.sx ? n0.x : n0.y, rb.fix, rb.fax);
+            tf0 = fminf(tf0, fmaf(rb.sy ? n0.z : n0.w, rb.fiy, rb.fay));
+            tf0 = fminf(tf0, fmaf(rb.sz ? n2.x : n2.y, rb.fiz, rb.faz));
+            tf0 = fminf(tf0, best.t);
+            // child 1
+            float tn1 = fmaf(rb.sx ? n1.y : n1.x, rb.nix, rb.nax);
+            tn1 = fmaxf(tn1, fmaf(rb.sy ? n1.w : n1.z, rb.niy, rb.nay));
+            tn1 = fmaxf(tn1, fmaf(rb.sz ? n2.w : n2.z, rb.niz, rb.naz));
+            tn1 = fmaxf(tn1, ray.tmin);
+            float tf1 = fmaf(rb.sx ? n1.x : n1.y, rb.fix, rb.fax);
+            tf1 = fminf(tf1, fmaf(rb.sy ? n1.z : n1.w, rb.fiy, rb.fay));
+            tf1 = fminf(tf1, fmaf(rb.sz ? n2.z : n2.w, rb.fiz, rb.faz));
+            tf1 = fminf(tf1, best.t);
+            const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
+            const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                const bool firstIs0 = tn0 <= tn1;          // near child first; ties -> child 0
+                cur = firstIs0 ? r0 : r1;
+                stack[sp++] = firstIs0 ? r1 : r0;
+            } else if (h0) cur = r0;
+            else if (h1) cur = r1;
+            else cur = sp ? stack[--sp] : kSentinel;
+        }
+        if (cur == kSentinel) break;
+        const int x = ~cur;
+        const int first = x >> 3, cnt = (x & 7) + 1;
+        for (int k = 0; k < cnt; k++) {
+            float t, u, v;
+            int prim;
+            if (COUNT) tc++;
+            if (triTest(tris + 3 * (size_t)(first + k), ray.o, ray.d, ray.tmin, best.t, t, u, v, prim)) {
+                if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
+            }
+        }
+        cur = sp ? stack[--sp] : kSentinel;
+        if (cur == kSentinel) break;
+    }
+    if (COUNT) { *nodeCount = nc; *triCount = tc; }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shading: closest hit (shaders.cu:779-811 live part; cuda/LocalGeometry.h:55-156) and the two
+// miss programs (shaders.cu:740-756).  params.lighting is hard-wired false in the reference
+// (libEyeRenderer.cpp:98), so the result is the base colour.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 linearize(V3 c) { return mk(crm::pow(c.x, 2.2f), crm::pow(c.y, 2.2f), crm::pow(c.z, 2.2f)); }
+
+__device__ __forceinline__ V3 shadeHit(const DeviceScene& sc, const Hit& h)
+{
+    const uint4 pr = __ldg(sc.prims + h.prim);
+    const MeshRec* m = sc.meshes + pr.w;
+    const float w0 = 1.0f - h.u - h.v;
+    if (m->colorType != -1) {
+        const float4 c0 = __ldg(sc.colors + pr.x), c1 = __ldg(sc.colors + pr.y), c2 = __ldg(sc.colors + pr.z);
+        const V3 col = mk(w0 * c0.x + h.u * c1.x + h.v * c2.x, w0 * c0.y + h.u * c1.y + h.v * c2.y,
+                          w0 * c0.z + h.u * c1.z + h.v * c2.z);
+        return linearize(col);
+    }
+    if (m->hasTex) {
+        float uu = h.u, vv = h.v;                                     // LocalGeometry.h:97-103
+        if (m->hasUV) {
+            const float2 t0 = __ldg(sc.uvs + pr.x), t1 = __ldg(sc.uvs + pr.y), t2 = __ldg(sc.uvs + pr.z);
+            uu = w0 * t0.x + h.u * t1.x + h.v * t2.x;
+            vv = w0 * t0.y + h.u * t1.y + h.v * t2.y;
+        }
+        const float4 tx = tex2D<float4>((cudaTextureObject_t)m->tex, uu, vv);
+        return linearize(mk(tx.x, tx.y, tx.z));
+    }
+    return mk(m->baseColor[0], m->baseColor[1], m->baseColor[2]);
+}
+
+__device__ __forceinline__ V3 shadeMiss(int shader, V3 rayDir)
+{
+    const V3 dir = vnormalize(rayDir);
+    if (shader == 1) {                                                // __miss__simple_sky
+        const float mix = fminf(fmaxf(0.0f, (crm::asin(dir.y) * 2.0f) / crm::kPi), 1.0f);
+        const float i255 = 1.0f / 255.0f;                             // sutil float3/float = * reciprocal
+        const V3 upper = mk(1.0f * i255, 31.0f * i255, 117.0f * i255);
+        const V3 lower = mk((143.0f * i255) * 0.8f, (179.0f * i255) * 0.8f, (203.0f * i255) * 0.8f);
+        return vadd(vmuls(lower, 1.0f - mix), vmuls(upper, mix));
+    }
+    const float border = 0.01f;                                       // __miss__default_background
+    if (fabsf(dir.x) < border || fabsf(dir.y) < border || fabsf(dir.z) < border) return mk(0.0f, 0.0f, 0.0f);
+    return mk((crm::atan2(dir.z, dir.x) + crm::kPi) / (crm::kPi * 2.0f), (crm::asin(dir.y) + crm::kPi / 2.0f) / crm::kPi, 0.0f);
+}
+
+__device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shaders.cu:180-189
+{
+    constexpr float ex = static_cast<float>(1.0 / static_cast<double>(2.2f));
+    return make_uchar4(static_cast<unsigned char>(crm::pow(fminf(fmaxf(r, 0.0f), 1.0f), ex) * 255.0f),
+                       static_cast<unsigned char>(crm::pow(fminf(fmaxf(g, 0.0f), 1.0f), ex) * 255.0f),
+                       static_cast<unsigned char>(crm::pow(fminf(fmaxf(b, 0.0f), 1.0f), ex) * 255.0f), 255u);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1.  One CTA owns a tile of `tileOmm` whole ommatidia (all their samples, in chunks of at most
+// kTileRays).  Lanes of a warp hold consecutive samples of one ommatidium -> coherent rays, one
+// coalesced 1 KB RNG-state read per warp.  Per-sample colour/S goes to shared memory and is then
+// summed IN SAMPLE ORDER by one thread per (ommatidium, channel): exactly the reference's
+// sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347) without its S*N*12-byte
+// global buffer round trip.
+// ------------------------------------------------------------------------------------------
+template <bool DUMP>
+__global__ void __launch_bounds__(kTraceThreads) k_traceCompound(const DeviceScene sc, const EyeParams ep)
+{
+    __shared__ float sR[kTileRays], sG[kTileRays], sB[kTileRays];
+    const float invS = 1.0f / (float)(uint32_t)ep.S;
+    for (int tile = blockIdx.x; tile < ep.nTiles; tile += gridDim.x) {
+        const int o0 = tile * ep.tileOmm;
+        const int nO = min(ep.tileOmm, ep.N - o0);
+        float carry = 0.0f;
+        for (int c0 = 0; c0 < ep.S; c0 += ep.chunk) {
+            const int nS = min(ep.chunk, ep.S - c0);
+            const int nRays = nO * nS;
+            for (int r = threadIdx.x; r < nRays; r += kTraceThreads) {
+                const int ol = r / nS;
+                const int s = c0 + (r - ol * nS);
+                const int o = o0 + ol;
+                const float4 q0 = __ldg(ep.omm + 2 * o), q1 = __ldg(ep.omm + 2 * o + 1);
+                uint4* statePtr = ep.rng + 2 * ((size_t)o * ep.S + s);
+                Rng rng = rngLoad(statePtr);
+                const Ray ray = ommatidialRay(q0, q1, ep.pose, rng);
+                rngStore(statePtr, rng);
+                const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, nullptr, nullptr);
+                const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
+                const float cr_ = col.x * invS, cg_ = col.y * invS, cb_ = col.z * invS;   // shaders.cu:730
+                sR[r] = cr_; sG[r] = cg_; sB[r] = cb_;
+                if (ep.samples) {
+                    float* dst = ep.samples + 3 * ((size_t)ep.N * s + o);
+                    dst[0] = cr_; dst[1] = cg_; dst[2] = cb_;
+                }
+                if (DUMP) {
+                    const size_t id = (size_t)ep.N * s + o;
+                    ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
+                    ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
+                    ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
+                }
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < 3 * nO; k += kTraceThreads) {
+                const int ol = k / 3, ch = k - 3 * ol;
+                const float* src = (ch == 0 ? sR : (ch == 1 ? sG : sB)) + ol * nS;
+                float sum = (c0 == 0) ? 0.0f : carry;       // carry is only live when nO == 1 (S > chunk)
+                for (int s = 0; s < nS; s++) sum += src[s];
+                carry = sum;
+                if (c0 + nS >= ep.S) reinterpret_cast<float*>(ep.summed + o0 + ol)[ch] = sum;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: vector projections (shaders.cu:375-406) and raw samples (shaders.cu:354-369)
+// ------------------------------------------------------------------------------------------
+__global__ void k_projectVector(int mode, const float4* __restrict__ summed, int N, uchar4* __restrict__ frame, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    uint32_t idx;
+    if (mode == PROJ_SINGLE_DIM_FAST) {
+        if (y > 0 || x >= N) return;                                  // other pixels keep their contents
+        idx = (uint32_t)x;
+    } else {
+        idx = (uint32_t)(((unsigned long long)(uint32_t)x * (unsigned long long)N) / (unsigned long long)(uint32_t)W);
+    }
+    const float4 c = __ldg(summed + idx);
+    frame[(size_t)y * W + x] = makeColor(c.x, c.y, c.z);
+}
+
+__global__ void k_projectRaw(const float* __restrict__ samples, int N, int S, uchar4* __restrict__ frame, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H || y >= S || x >= N) return;
+    const float* p = samples + 3 * ((size_t)N * y + x);
+    frame[(size_t)y * W + x] = makeColor(p[0], p[1], p[2]);
+}
+
+__global__ void k_packRow(const float4* __restrict__ summed, int N, uchar4* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= N) return;
+    const float4 c = __ldg(summed + x);
+    out[x] = makeColor(c.x, c.y, c.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: nearest-ommatidium map of the spherical projections (shaders.cu:412-448, 454-490, 496-541,
+// 548-593, 600-640): first index minimising acos(dot(a,v)/(|a||v|)), strict '<', NaN never wins,
+// index 0 is the unconditional initial candidate.  The map depends only on (eye, W, H, mode), so
+// it is built once and cached instead of being recomputed per frame (O(W*H*N) acos).
+// ------------------------------------------------------------------------------------------
+constexpr int kMapThreads = 128;
+
+__global__ void __launch_bounds__(kMapThreads)
+k_buildProjectionMap(int mode, const float4* __restrict__ omm, int N, uint32_t* __restrict__ map, int W, int H)
+{
+    __shared__ float4 sA[kMapThreads];     // (a.xyz, |a|)
+    __shared__ float sPx[kMapThreads];     // relativePosition.x (split eligibility)
+    const long long p = (long long)blockIdx.x * kMapThreads + threadIdx.x;
+    const bool live = p < (long long)W * H;
+    const int x = live ? (int)(p % W) : 0, y = live ? (int)(p / W) : 0;
+    const float uvx = (float)x / (float)W;
+    float dx, dy;
+    if (mode == PROJ_SPH_SPLIT_ORIENTATIONWISE) {                     // shaders.cu:505-513
+        const float sx = uvx * 2.0f, sy = ((float)y / (float)H) * 1.0f;
+        const float sub = sx > 1.0f ? 1.0f : 0.0f;
+        dx = (sx - sub) * 2.0f - 1.0f;
+        dy = sy * 2.0f - 1.0f;
+    } else {
+        dx = 2.0f * uvx - 1.0f;
+        dy = 2.0f * ((float)y / (float)H) - 1.0f;
+    }
+    const float ax = dx * (-crm::kPi) + crm::kPi / 2.0f;
+    const float ay = dy * (crm::kPi / 2.0f) + 0.0f;
+    float sax, cax, say, cay;
+    crm::sincos(ax, sax, cax);
+    crm::sincos(ay, say, cay);
+    const V3 usp = mk(cax * cay, say, sax * cay);
+    const float lu = vlen(usp);
+    const bool byPos = (mode == PROJ_SPH_POSITIONWISE || mode == PROJ_SPH_POSITIONWISE_IDS);
+    const bool split = (mode == PROJ_SPH_SPLIT_ORIENTATIONWISE);
+    uint32_t closest = 0;
+    float smallest = 0.0f;
+    for (int base = 0; base < N; base += kMapThreads) {
+        const int i = base + threadIdx.x;
+        __syncthreads();
+        if (i < N) {
+            const float4 q0 = __ldg(omm + 2 * i), q1 = __ldg(omm + 2 * i + 1);
+            const V3 a = byPos ? mk(q0.x, q0.y, q0.z) : mk(q0.w, q1.x, q1.y);
+            sA[threadIdx.x] = make_float4(a.x, a.y, a.z, vlen(a));
+            sPx[threadIdx.x] = q0.x;
+        }
+        __syncthreads();
+        const int cnt = min(kMapThreads, N - base);
+        for (int k = 0; k < cnt; k++) {
+            const float4 a = sA[k];
+            const float ang = crm::acos(vdot(mk(a.x, a.y, a.z), usp) / (a.w * lu));
+            const int idx = base + k;
+            if (idx == 0) { smallest = ang; continue; }
+            bool eligible = true;
+            if (split) { const float px = sPx[k]; eligible = (px > 0.0f && uvx > 0.5f) || (px < 0.0f && uvx < 0.5f); }
+            if (eligible && ang < smallest) { smallest = ang; closest = (uint32_t)idx; }
+        }
+    }
+    if (live) map[p] = closest;
+}
+
+__global__ void k_projectMap(bool ids, const uint32_t* __restrict__ map, const float4* __restrict__ summed,
+                             uchar4* __restrict__ frame, long long nPix)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPix) return;
+    const uint32_t idx = __ldg(map + p);
+    if (ids) {                                                        // shaders.cu:583-592
+        frame[p] = make_uchar4((unsigned char)(idx >> 24), (unsigned char)((idx >> 16) & 0xff),
+                               (unsigned char)((idx >> 8) & 0xff), (unsigned char)(idx & 0xff));
+    } else {
+        const float4 c = __ldg(summed + idx);
+        frame[p] = makeColor(c.x, c.y, c.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: ordinary cameras (shaders.cu:198-333), tmin 0.01, one primary ray per pixel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1, float s2, uchar4* __restrict__ frame, int W, int H)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)W * H) return;
+    const int x = (int)(p % W), y = (int)(p / W);
+    const float dx = 2.0f * (((float)x + 0.0f) / (float)W) - 1.0f;
+    const float dy = 2.0f * (((float)y + 0.0f) / (float)H) - 1.0f;
+    const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz), C = mk(P.px, P.py, P.pz);
+    Ray ray;
+    if (kind == 0) {
+        ray.d = vadd(vadd(vmuls(Z, s2), vmuls(vmuls(X, dx), s0)), vmuls(vmuls(Y, dy), s1));
+        ray.o = C;
+    } else if (kind == 1) {
+        const float ax = dx * (-crm::kPi) + crm::kPi / 2.0f, ay = dy * (crm::kPi / 2.0f) + 0.0f;
+        float sax, cax, say, cay;
+        crm::sincos(ax, sax, cax);
+        crm::sincos(ay, say, cay);
+        const V3 od = mk(cax * cay, say, sax * cay);
+        ray.d = vnormalize(vadd(vadd(vmuls(X, od.x), vmuls(Y, od.y)), vmuls(Z, od.z)));
+        ray.o = vadd(C, vmuls(ray.d, s0));
+    } else {
+        ray.d = Z;
+        ray.o = vadd(vadd(C, vmuls(vmuls(X, dx), s0)), vmuls(vmuls(Y, dy), s1));
+    }
+    ray.tmin = 0.01f;
+    const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, nullptr, nullptr);
+    const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
+    frame[p] = makeColor(col.x, col.y, col.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// Debug / parity kernels (reached only through the crDebug* calls)
+// ------------------------------------------------------------------------------------------
+__global__ void k_traceRays(const DeviceScene sc, const float* __restrict__ origins, const float* __restrict__ dirs,
+                            const float* __restrict__ tmins, int n, int4* __restrict__ hits)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray ray;
+    ray.o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+    ray.d = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+    ray.tmin = tmins[i];
+    int nc = 0, tc = 0;
+    const Hit h = traceClosest<true>(sc.nodes, sc.tris, ray, kTMax, &nc, &tc);
+    hits[2 * i] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
+    hits[2 * i + 1] = make_int4(nc, tc, 0, 0);
+}
+
+__global__ void k_evalMath(int fn, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = a[i], y = b ? b[i] : 0.0f;
+    float r = 0.0f, s, c;
+    switch (fn) {
+        case 0: crm::sincos(x, s, c); r = s; break;
+        case 1: crm::sincos(x, s, c); r = c; break;
+        case 2: r = crm::log(x); break;
+        case 3: r = crm::exp(x); break;
+        case 4: r = crm::pow(x, y); break;
+        case 5: r = crm::asin(x); break;
+        case 6: r = crm::acos(x); break;
+        case 7: r = crm::atan2(x, y); break;
+        default: break;
+    }
+    out[i] = r;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cudaStream_t stream)
+{
+    const long long n = (long long)N * S;
+    if (n <= 0) return;
+    const int tpb = 128;
+    k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame);
+}
+
+void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream)
+{
+    if (eye.nTiles <= 0) return;
+    const int grid = gridBlocks < eye.nTiles ? gridBlocks : eye.nTiles;
+    if (eye.dumpHits) k_traceCompound<true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    else k_traceCompound<false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+}
+
+int traceKernelOccupancy()
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false>, kTraceThreads, 0);
+    return n > 0 ? n : 1;
+}
+
+void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream)
+{
+    if (W <= 0 || H <= 0) return;
+    const int rows = (mode == PROJ_SINGLE_DIM_FAST) ? 1 : H;
+    dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows);
+    k_projectVector<<<grid, 128, 0, stream>>>(mode, summed, N, frame, W, H);
+}
+
+void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream)
+{
+    if (W <= 0 || H <= 0) return;
+    const int rows = H < S ? H : S;
+    dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows);
+    k_projectRaw<<<grid, 128, 0, stream>>>(samples, N, S, frame, W, H);
+}
+
+void launchPackRow(const float4* summed, int N, uchar4* out, cudaStream_t stream)
+{
+    if (N <= 0) return;
+    k_packRow<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(summed, N, out);
+}
+
+void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream)
+{
+    const long long nPix = (long long)W * H;
+    if (nPix <= 0) return;
+    k_buildProjectionMap<<<(unsigned)((nPix + kMapThreads - 1) / kMapThreads), kMapThreads, 0, stream>>>(mode, omm, N, map, W, H);
+}
+
+void launchProjectMap(bool ids, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream)
+{
+    const long long nPix = (long long)W * H;
+    if (nPix <= 0) return;
+    k_projectMap<<<(unsigned)((nPix + 255) / 256), 256, 0, stream>>>(ids, map, summed, frame, nPix);
+}
+
+void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame, int W,
+                  int H, cudaStream_t stream)
+{
+    const long long nPix = (long long)W * H;
+    if (nPix <= 0) return;
+    k_camera<<<(unsigned)((nPix + 127) / 128), 128, 0, stream>>>(sc, kind, pose, s0, s1, s2, frame, W, H);
+}
+
+void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,
+                     cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_traceRays<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, origins, dirs, tmins, n, hits);
+}
+
+void launchEvalMath(int fn, const float* a, const float* b, float* out, int n, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_evalMath<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fn, a, b, out, n);
+}
+
+}  // namespace cr

@@ -1,0 +1,646 @@
+// cr_renderer.cu -- host orchestration: device buffers, frame loop, pose batches, debug access.
+// See cr_renderer.h for the reference code this replaces.
+#include "cr_renderer.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+
+namespace cr {
+
+#define CR_CUDA(x)                                                                                          \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess)                                                                              \
+            throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(e_) + " at " #x);     \
+    } while (0)
+
+namespace {
+template <typename T>
+T* dallocT(size_t n)
+{
+    T* p = nullptr;
+    CR_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+    return p;
+}
+template <typename T>
+void dfree(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+int projectionFromName(const std::string& n)
+{
+    if (n == "raw_ommatidial_samples") return PROJ_RAW_SAMPLES;
+    if (n == "single_dimension") return PROJ_SINGLE_DIM;
+    if (n == "single_dimension_fast") return PROJ_SINGLE_DIM_FAST;
+    if (n == "spherical_positionwise") return PROJ_SPH_POSITIONWISE;
+    if (n == "spherical_orientationwise") return PROJ_SPH_ORIENTATIONWISE;
+    if (n == "spherical_split_orientationwise") return PROJ_SPH_SPLIT_ORIENTATIONWISE;
+    if (n == "spherical_orientationwise_ids") return PROJ_SPH_ORIENTATIONWISE_IDS;
+    if (n == "spherical_positionwise_ids") return PROJ_SPH_POSITIONWISE_IDS;
+    return PROJ_UNKNOWN;
+}
+}  // namespace
+
+Renderer& renderer()
+{
+    static Renderer r;
+    return r;
+}
+
+Renderer::Renderer() {}
+Renderer::~Renderer()
+{
+    // process teardown: the CUDA context may already be gone; do not touch the device here
+}
+
+void Renderer::setDevice(int dev)
+{
+    if (deviceReady_ && dev != device_) throw std::runtime_error("crSetDevice must be called before the first GPU use");
+    device_ = dev;
+}
+
+void Renderer::ensureDevice()
+{
+    if (deviceReady_) { CR_CUDA(cudaSetDevice(device_)); return; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw std::runtime_error("no CUDA device available: this renderer has no CPU path (sm_100a kernels only)");
+    if (device_ < 0) {
+        const char* env = getenv("CR_DEVICE");
+        device_ = env ? atoi(env) : 0;
+    }
+    if (device_ >= count) throw std::runtime_error("requested CUDA device index out of range");
+    CR_CUDA(cudaSetDevice(device_));
+    CR_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CR_CUDA(cudaEventCreate(&evA_));
+    CR_CUDA(cudaEventCreate(&evB_));
+    cudaDeviceProp prop;
+    CR_CUDA(cudaGetDeviceProperties(&prop, device_));
+    numSMs_ = prop.multiProcessorCount;
+    traceOcc_ = traceKernelOccupancy();
+    deviceReady_ = true;
+    if (verbose)
+        std::cout << "[PyEye] CUDA device " << device_ << ": " << prop.name << ", " << numSMs_ << " SMs, trace kernel "
+                  << traceOcc_ << " CTAs/SM" << std::endl;
+}
+
+DevicePose Renderer::toDevicePose(const Pose& p)
+{
+    DevicePose d;
+    d.px = p.pos.x; d.py = p.pos.y; d.pz = p.pos.z;
+    d.xx = p.ax.x; d.xy = p.ax.y; d.xz = p.ax.z;
+    d.yx = p.ay.x; d.yy = p.ay.y; d.yz = p.ay.z;
+    d.zx = p.az.x; d.zy = p.az.y; d.zz = p.az.z;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+void Renderer::freeCompound(CompoundState& cs)
+{
+    dfree(cs.dOmm); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
+    dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
+    cs.dumpCap = 0;
+    cs.rngN = cs.rngS = 0;
+    cs.mapMode = -2;
+}
+
+void Renderer::freeScene()
+{
+    if (!deviceReady_) return;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (auto& kv : compound_) freeCompound(kv.second);
+    compound_.clear();
+    for (auto t : texObjects_) cudaDestroyTextureObject(t);
+    for (auto a : texArrays_) cudaFreeArray(a);
+    texObjects_.clear();
+    texArrays_.clear();
+    dfree(bvh_.nodes); dfree(bvh_.tris);
+    bvh_ = BvhBuildResult();
+    dfree(dPositions_); dfree(dIndices_); dfree(dPrims_); dfree(dUvs_); dfree(dColors_); dfree(dMeshes_);
+    dscene_ = DeviceScene();
+}
+
+void Renderer::stop()
+{
+    if (verbose) std::cout << "[PyEye] Cleaning eye renderer resources." << std::endl;
+    freeScene();
+    if (deviceReady_) {
+        dfree(dFrame_);
+        if (hFrame_) cudaFreeHost(hFrame_);
+        hFrame_ = nullptr;
+        frameCap_ = 0;
+        frameW_ = frameH_ = 0;
+    }
+    scene_ = HostScene();
+    loaded_ = false;
+    current_ = 0;
+}
+
+void Renderer::loadScene(const std::string& path)
+{
+    HostScene sc = loadGltfScene(path, verbose);
+    freeScene();
+    scene_ = std::move(sc);
+    loaded_ = true;
+    current_ = 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0) {
+        ensureDevice();
+        uploadScene();
+    } else if (verbose) {
+        std::cout << "[PyEye] no CUDA device visible: scene parsed on the host only; rendering will fail." << std::endl;
+    }
+}
+
+void Renderer::uploadScene()
+{
+    const size_t T = scene_.triangleCount(), V = scene_.vertexCount();
+    float smin[3] = {0, 0, 0}, smax[3] = {0, 0, 0};
+    if (V) {
+        for (int a = 0; a < 3; a++) { smin[a] = INFINITY; smax[a] = -INFINITY; }
+        for (size_t v = 0; v < V; v++)
+            for (int a = 0; a < 3; a++) {
+                const float p = scene_.positions[3 * v + a];
+                smin[a] = fminf(smin[a], p);
+                smax[a] = fmaxf(smax[a], p);
+            }
+    }
+    dPositions_ = dallocT<float>(3 * V);
+    dIndices_ = dallocT<uint32_t>(3 * T);
+    if (V) CR_CUDA(cudaMemcpyAsync(dPositions_, scene_.positions.data(), sizeof(float) * 3 * V, cudaMemcpyHostToDevice, stream_));
+    if (T) CR_CUDA(cudaMemcpyAsync(dIndices_, scene_.indices.data(), sizeof(uint32_t) * 3 * T, cudaMemcpyHostToDevice, stream_));
+    int leafSize = 4;
+    if (const char* env = getenv("CR_LEAF_SIZE")) leafSize = atoi(env);
+    bvh_ = buildLbvh(dPositions_, dIndices_, static_cast<int>(T), smin, smax, leafSize, stream_);
+    dfree(dPositions_);
+    dfree(dIndices_);
+
+    std::vector<uint4> prims(T);
+    for (size_t t = 0; t < T; t++)
+        prims[t] = make_uint4(scene_.indices[3 * t], scene_.indices[3 * t + 1], scene_.indices[3 * t + 2], scene_.triMesh[t]);
+    dPrims_ = dallocT<uint4>(T);
+    if (T) CR_CUDA(cudaMemcpyAsync(dPrims_, prims.data(), sizeof(uint4) * T, cudaMemcpyHostToDevice, stream_));
+    if (scene_.anyUV) {
+        dUvs_ = dallocT<float2>(V);
+        CR_CUDA(cudaMemcpyAsync(dUvs_, scene_.uvs.data(), sizeof(float) * 2 * V, cudaMemcpyHostToDevice, stream_));
+    }
+    if (scene_.anyColor) {
+        dColors_ = dallocT<float4>(V);
+        CR_CUDA(cudaMemcpyAsync(dColors_, scene_.colors.data(), sizeof(float) * 4 * V, cudaMemcpyHostToDevice, stream_));
+    }
+    // textures: wrap + bilinear + normalised float reads, the only sampler the reference can create
+    // (MulticamScene.cpp:801-834)
+    for (const ImageRGBA8& img : scene_.textures) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        CR_CUDA(cudaMallocArray(&arr, &desc, static_cast<size_t>(img.width), static_cast<size_t>(img.height)));
+        const size_t pitch = static_cast<size_t>(img.width) * 4;
+        CR_CUDA(cudaMemcpy2DToArray(arr, 0, 0, img.pixels.data(), pitch, pitch, static_cast<size_t>(img.height), cudaMemcpyHostToDevice));
+        cudaResourceDesc res = {};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = cudaAddressModeWrap;
+        td.addressMode[1] = cudaAddressModeWrap;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        td.maxAnisotropy = 1;
+        td.sRGB = 0;
+        cudaTextureObject_t tex = 0;
+        CR_CUDA(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        texArrays_.push_back(arr);
+        texObjects_.push_back(tex);
+    }
+    std::vector<MeshRec> recs(scene_.meshes.size());
+    for (size_t i = 0; i < recs.size(); i++) {
+        const MeshGroup& m = scene_.meshes[i];
+        MeshRec& r = recs[i];
+        r.colorType = m.colorType;
+        r.hasUV = m.hasUV;
+        r.hasTex = (m.texture >= 0 && static_cast<size_t>(m.texture) < texObjects_.size()) ? 1 : 0;
+        r.pad = 0;
+        r.tex = r.hasTex ? static_cast<unsigned long long>(texObjects_[static_cast<size_t>(m.texture)]) : 0ull;
+        memcpy(r.baseColor, m.baseColor, sizeof r.baseColor);
+    }
+    dMeshes_ = dallocT<MeshRec>(recs.size());
+    if (!recs.empty()) CR_CUDA(cudaMemcpyAsync(dMeshes_, recs.data(), sizeof(MeshRec) * recs.size(), cudaMemcpyHostToDevice, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+
+    dscene_.nodes = bvh_.nodes;
+    dscene_.tris = bvh_.tris;
+    dscene_.prims = dPrims_;
+    dscene_.uvs = dUvs_;
+    dscene_.colors = dColors_;
+    dscene_.meshes = dMeshes_;
+    dscene_.nNodes = bvh_.nNodes;
+    dscene_.nTris = bvh_.nTris;
+    dscene_.missShader = scene_.missShader;
+    if (verbose)
+        std::cout << "[PyEye] scene on device: " << T << " triangles, " << bvh_.nNodes << " BVH nodes, built in "
+                  << bvh_.buildMs << " ms" << std::endl;
+}
+
+// ------------------------------------------------------------------------------------------
+HostCamera& Renderer::camera()
+{
+    if (scene_.cameras.empty()) {                                     // MulticamScene.cpp:911-927
+        std::cerr << "Initializing default camera" << std::endl;
+        HostCamera c;
+        c.name = "Default Camera";
+        c.kind = CAM_PERSPECTIVE;
+        scene_.cameras.push_back(c);
+    }
+    if (current_ >= scene_.cameras.size()) current_ = 0;
+    return scene_.cameras[current_];
+}
+size_t Renderer::cameraCount() { return scene_.cameras.size(); }
+void Renderer::setCurrentCamera(int index)
+{
+    const int s = static_cast<int>(cameraCount());
+    if (s == 0) { current_ = 0; return; }
+    current_ = static_cast<size_t>((index % s + s) % s);            // MulticamScene.cpp:929-934
+}
+bool Renderer::compoundActive() { return camera().kind == CAM_COMPOUND; }
+
+CompoundState& Renderer::compoundState(size_t camIdx)
+{
+    auto it = compound_.find(camIdx);
+    if (it == compound_.end()) {
+        CompoundState cs;
+        cs.N = static_cast<int>(scene_.cameras[camIdx].ommatidia.size());
+        it = compound_.emplace(camIdx, cs).first;
+    }
+    return it->second;
+}
+
+void Renderer::setSamples(int s)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    cs.S = std::max(1, s);                                            // CompoundEye.cpp:171-183
+    cs.randomsConfigured = false;
+}
+int Renderer::samples()
+{
+    if (!compoundActive()) return -1;
+    return compoundState(current_).S;
+}
+size_t Renderer::ommatidialCount()
+{
+    if (!compoundActive()) return 0;
+    return camera().ommatidia.size();
+}
+void Renderer::setOmmatidia(const Ommatidium* omm, size_t count)
+{
+    if (!compoundActive()) return;
+    HostCamera& cam = camera();
+    CompoundState& cs = compoundState(current_);
+    if (count != cam.ommatidia.size()) cs.randomsConfigured = false;  // CompoundEye.cpp:35-48
+    cam.ommatidia.assign(omm, omm + count);
+    cs.N = static_cast<int>(count);
+    cs.ommDirty = true;
+    cs.eyeVersion++;
+}
+void Renderer::setFirstFrame(uint64_t k)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    cs.firstFrame = k;
+    cs.randomsConfigured = false;
+}
+
+void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
+{
+    const int N = static_cast<int>(cam.ommatidia.size());
+    cs.N = N;
+    if (cs.ommDirty || !cs.dOmm) {
+        dfree(cs.dOmm);
+        cs.dOmm = dallocT<float4>(2 * static_cast<size_t>(N));
+        CR_CUDA(cudaMemcpyAsync(cs.dOmm, cam.ommatidia.data(), sizeof(Ommatidium) * static_cast<size_t>(N), cudaMemcpyHostToDevice, stream_));
+        cs.ommDirty = false;
+    }
+    if (cs.rngN != N || cs.rngS != cs.S || !cs.dRng) {
+        dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples);
+        cs.dRng = dallocT<uint4>(2 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
+        cs.dSummed = dallocT<float4>(static_cast<size_t>(N));
+        CR_CUDA(cudaMemsetAsync(cs.dSummed, 0, sizeof(float4) * static_cast<size_t>(N ? N : 1), stream_));
+        cs.rngN = N;
+        cs.rngS = cs.S;
+        cs.randomsConfigured = false;
+    }
+    if (!cs.randomsConfigured) {
+        launchRngInit(cs.dRng, N, cs.S, cs.firstFrame, stream_);
+        launches_++;
+        cs.frameIndex = cs.firstFrame;
+        cs.randomsConfigured = true;
+    }
+}
+
+void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose)
+{
+    EyeParams ep;
+    ep.omm = cs.dOmm;
+    ep.rng = cs.dRng;
+    ep.summed = cs.dSummed;
+    ep.N = cs.N;
+    ep.S = cs.S;
+    ep.pose = toDevicePose(pose);
+    const int mode = projectionFromName(cam.projection);
+    if (mode == PROJ_RAW_SAMPLES) {
+        if (!cs.dSamples) cs.dSamples = dallocT<float>(3 * static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S));
+        ep.samples = cs.dSamples;
+    }
+    if (dumpRays) {
+        const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
+        if (cs.dumpCap < need) {
+            dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
+            cs.dDumpO = dallocT<float>(3 * need);
+            cs.dDumpD = dallocT<float>(3 * need);
+            cs.dDumpH = dallocT<int4>(need);
+            cs.dumpCap = need;
+        }
+        ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH;
+    }
+    // tiling: whole ommatidia per CTA tile, enough tiles to fill the machine when the frame allows
+    const long long totalRays = static_cast<long long>(cs.N) * cs.S;
+    const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
+    long long target = totalRays / (slots > 0 ? slots : 1);
+    target = std::max<long long>(kTraceThreads, std::min<long long>(kTileRays, target));
+    if (cs.S >= kTileRays) { ep.chunk = kTileRays; ep.tileOmm = 1; }
+    else {
+        ep.chunk = cs.S;
+        ep.tileOmm = static_cast<int>(std::max<long long>(1, std::min<long long>(kTileRays / cs.S, target / cs.S)));
+    }
+    ep.nTiles = (cs.N + ep.tileOmm - 1) / ep.tileOmm;
+    launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
+    launches_++;
+    cs.frameIndex++;
+}
+
+void Renderer::project(CompoundState& cs, const HostCamera& cam)
+{
+    const int mode = projectionFromName(cam.projection);
+    switch (mode) {
+        case PROJ_RAW_SAMPLES:
+            launchProjectRaw(cs.dSamples, cs.N, cs.S, dFrame_, W_, H_, stream_);
+            launches_++;
+            break;
+        case PROJ_SINGLE_DIM:
+        case PROJ_SINGLE_DIM_FAST:
+            launchProjectVector(mode, cs.dSummed, cs.N, dFrame_, W_, H_, stream_);
+            launches_++;
+            break;
+        case PROJ_UNKNOWN:
+            std::cerr << "[PyEye] ERROR: unknown compound projection shader '__raygen__compound_projection_" << cam.projection
+                      << "'; frame left untouched." << std::endl;
+            break;
+        default: {
+            if (!cs.dMap || cs.mapMode != mode || cs.mapW != W_ || cs.mapH != H_ || cs.mapEyeVersion != cs.eyeVersion) {
+                dfree(cs.dMap);
+                cs.dMap = dallocT<uint32_t>(static_cast<size_t>(W_) * static_cast<size_t>(H_));
+                launchBuildProjectionMap(mode, cs.dOmm, cs.N, cs.dMap, W_, H_, stream_);
+                launches_++;
+                cs.mapMode = mode; cs.mapW = W_; cs.mapH = H_; cs.mapEyeVersion = cs.eyeVersion;
+            }
+            const bool ids = (mode == PROJ_SPH_ORIENTATIONWISE_IDS || mode == PROJ_SPH_POSITIONWISE_IDS);
+            launchProjectMap(ids, cs.dMap, cs.dSummed, dFrame_, W_, H_, stream_);
+            launches_++;
+            break;
+        }
+    }
+}
+
+void Renderer::ensureFrame()
+{
+    const size_t need = static_cast<size_t>(W_) * static_cast<size_t>(H_);
+    if (dFrame_ && frameW_ == W_ && frameH_ == H_) return;
+    dfree(dFrame_);
+    if (hFrame_) cudaFreeHost(hFrame_);
+    hFrame_ = nullptr;
+    dFrame_ = dallocT<uchar4>(need);
+    CR_CUDA(cudaMemsetAsync(dFrame_, 0, sizeof(uchar4) * (need ? need : 1), stream_));
+    CR_CUDA(cudaMallocHost(&hFrame_, sizeof(uchar4) * (need ? need : 1)));
+    memset(hFrame_, 0, sizeof(uchar4) * (need ? need : 1));
+    frameCap_ = need;
+    frameW_ = W_;
+    frameH_ = H_;
+}
+
+void Renderer::setRenderSize(int w, int h)
+{
+    W_ = std::max(0, w);
+    H_ = std::max(0, h);
+    if (verbose) std::cout << "[PyEye] Resizing rendering buffer to (" << w << ", " << h << ")." << std::endl;
+}
+
+double Renderer::renderFrame()
+{
+    if (!loaded_) throw std::runtime_error("renderFrame called before loadGlTFscene");
+    ensureDevice();
+    if (!dscene_.nodes) uploadScene();
+    ensureFrame();
+    HostCamera& cam = camera();
+    const auto t0 = std::chrono::steady_clock::now();
+    bool timedTrace = false;
+    if (cam.kind == CAM_COMPOUND) {
+        CompoundState& cs = compoundState(current_);
+        prepareCompound(cs, cam);
+        CR_CUDA(cudaEventRecord(evA_, stream_));
+        launchCompound(cs, cam, cam.pose);
+        CR_CUDA(cudaEventRecord(evB_, stream_));
+        timedTrace = true;
+        project(cs, cam);
+    } else {
+        launchCamera(dscene_, static_cast<int>(cam.kind), toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
+                     W_, H_, stream_);
+        launches_++;
+    }
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    CR_CUDA(cudaGetLastError());
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (timedTrace) {
+        float k = 0.0f;
+        cudaEventElapsedTime(&k, evA_, evB_);
+        lastTraceMs_ = k;
+    }
+    if (verbose) std::cout << "[PyEye] Rendered frame in " << ms << "ms." << std::endl;
+    return ms;
+}
+
+unsigned char* Renderer::framePointer()
+{
+    if (verbose) std::cout << "[PyEye] Retrieving frame pointer..." << std::endl;
+    ensureDevice();
+    ensureFrame();
+    CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    return hFrame_;
+}
+
+void Renderer::saveFrame(const std::string& path)
+{
+    // binary P6, RGB, flipped to top-down (sutil/sutil.cpp:82-102, 387-412)
+    const unsigned char* px = framePointer();
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    f << "P6\n" << W_ << " " << H_ << "\n255\n";
+    std::vector<unsigned char> row(static_cast<size_t>(W_) * 3);
+    for (int y = H_ - 1; y >= 0; y--) {
+        for (int x = 0; x < W_; x++) {
+            const unsigned char* p = px + 4 * (static_cast<size_t>(y) * W_ + x);
+            row[3 * x] = p[0]; row[3 * x + 1] = p[1]; row[3 * x + 2] = p[2];
+        }
+        f.write(reinterpret_cast<const char*>(row.data()), static_cast<std::streamsize>(row.size()));
+    }
+    if (verbose) std::cout << "[PyEye] Saved render as '" << path << "'" << std::endl;
+}
+
+// ------------------------------------------------------------------------------------------
+// additive API
+// ------------------------------------------------------------------------------------------
+void Renderer::copyOmmatidialData(float* outRgb)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    if (!cs.dSummed) return;
+    std::vector<float4> tmp(static_cast<size_t>(cs.N));
+    CR_CUDA(cudaMemcpyAsync(tmp.data(), cs.dSummed, sizeof(float4) * tmp.size(), cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    for (size_t i = 0; i < tmp.size(); i++) { outRgb[3 * i] = tmp[i].x; outRgb[3 * i + 1] = tmp[i].y; outRgb[3 * i + 2] = tmp[i].z; }
+}
+
+// Renders `count` consecutive frames of the current compound eye, one per pose (12 floats each:
+// position, x, y, z axes), exactly as `count` calls of setCameraPosition/LocalSpace + renderFrame
+// would, but without per-frame host synchronisation.  Row p of the result is the
+// single_dimension_fast row of pose p (uchar4 per ommatidium).  The result goes to `outDevice`
+// (device pointer, e.g. a collective's send slot) when non-null, else to host `outRgba`.
+double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned char* outRgba, void* outDevice)
+{
+    if (!loaded_) throw std::runtime_error("renderPoseBatch called before loadGlTFscene");
+    if (!compoundActive()) throw std::runtime_error("renderPoseBatch needs an active compound eye");
+    ensureDevice();
+    if (!dscene_.nodes) uploadScene();
+    HostCamera& cam = camera();
+    CompoundState& cs = compoundState(current_);
+    const auto t0 = std::chrono::steady_clock::now();
+    prepareCompound(cs, cam);
+    const size_t N = static_cast<size_t>(cs.N);
+    uchar4* dOut = static_cast<uchar4*>(outDevice);
+    uchar4* dTmp = nullptr;
+    if (!dOut) { dTmp = dallocT<uchar4>(N * count); dOut = dTmp; }
+    CR_CUDA(cudaEventRecord(evA_, stream_));
+    for (size_t p = 0; p < count; p++) {
+        Pose pose;
+        const float* q = poses12 + 12 * p;
+        pose.pos = {q[0], q[1], q[2]};
+        pose.ax = {q[3], q[4], q[5]};
+        pose.ay = {q[6], q[7], q[8]};
+        pose.az = {q[9], q[10], q[11]};
+        launchCompound(cs, cam, pose);
+        launchPackRow(cs.dSummed, cs.N, dOut + p * N, stream_);
+        launches_++;
+    }
+    CR_CUDA(cudaEventRecord(evB_, stream_));
+    if (outRgba) CR_CUDA(cudaMemcpyAsync(outRgba, dOut, sizeof(uchar4) * N * count, cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    CR_CUDA(cudaGetLastError());
+    float k = 0.0f;
+    cudaEventElapsedTime(&k, evA_, evB_);
+    lastTraceMs_ = k;
+    dfree(dTmp);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / parity access
+// ------------------------------------------------------------------------------------------
+void Renderer::debugCopyBvh(float* nodes, float* tris)
+{
+    ensureDevice();
+    if (!dscene_.nodes) uploadScene();
+    if (nodes) CR_CUDA(cudaMemcpy(nodes, bvh_.nodes, sizeof(float4) * 4 * static_cast<size_t>(bvh_.nNodes), cudaMemcpyDeviceToHost));
+    if (tris && bvh_.nTris) CR_CUDA(cudaMemcpy(tris, bvh_.tris, sizeof(float4) * 3 * static_cast<size_t>(bvh_.nTris), cudaMemcpyDeviceToHost));
+}
+
+void Renderer::debugCopyRngStates(uint32_t* out8)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    if (!cs.dRng) return;
+    const size_t N = static_cast<size_t>(cs.rngN), S = static_cast<size_t>(cs.rngS);
+    std::vector<uint32_t> tmp(8 * N * S);
+    CR_CUDA(cudaMemcpyAsync(tmp.data(), cs.dRng, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    for (size_t o = 0; o < N; o++)
+        for (size_t s = 0; s < S; s++)
+            memcpy(out8 + 8 * (N * s + o), tmp.data() + 8 * (o * S + s), 32);
+}
+
+size_t Renderer::debugCopyLastRays(float* origins, float* dirs, int32_t* hits4)
+{
+    if (!compoundActive()) return 0;
+    CompoundState& cs = compoundState(current_);
+    const size_t n = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
+    if (!cs.dDumpH || cs.dumpCap < n) return 0;
+    CR_CUDA(cudaMemcpy(origins, cs.dDumpO, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    CR_CUDA(cudaMemcpy(dirs, cs.dDumpD, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    CR_CUDA(cudaMemcpy(hits4, cs.dDumpH, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+void Renderer::debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8)
+{
+    ensureDevice();
+    if (!loaded_) throw std::runtime_error("no scene loaded");
+    if (!dscene_.nodes) uploadScene();
+    float* dO = dallocT<float>(3 * static_cast<size_t>(n));
+    float* dD = dallocT<float>(3 * static_cast<size_t>(n));
+    float* dT = dallocT<float>(static_cast<size_t>(n));
+    int4* dH = dallocT<int4>(2 * static_cast<size_t>(n));
+    CR_CUDA(cudaMemcpyAsync(dO, origins, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, stream_));
+    CR_CUDA(cudaMemcpyAsync(dD, dirs, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, stream_));
+    CR_CUDA(cudaMemcpyAsync(dT, tmins, sizeof(float) * n, cudaMemcpyHostToDevice, stream_));
+    launchTraceRays(dscene_, dO, dD, dT, n, dH, stream_);
+    launches_++;
+    CR_CUDA(cudaMemcpyAsync(hits8, dH, sizeof(int4) * 2 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    CR_CUDA(cudaGetLastError());
+    dfree(dO); dfree(dD); dfree(dT); dfree(dH);
+}
+
+void Renderer::debugCopyProjectionMap(uint32_t* out)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    if (!cs.dMap) return;
+    CR_CUDA(cudaMemcpy(out, cs.dMap, sizeof(uint32_t) * static_cast<size_t>(cs.mapW) * static_cast<size_t>(cs.mapH), cudaMemcpyDeviceToHost));
+}
+
+void Renderer::debugEvalMath(int fn, const float* a, const float* b, float* out, int n)
+{
+    ensureDevice();
+    float* dA = dallocT<float>(static_cast<size_t>(n));
+    float* dB = b ? dallocT<float>(static_cast<size_t>(n)) : nullptr;
+    float* dO = dallocT<float>(static_cast<size_t>(n));
+    CR_CUDA(cudaMemcpyAsync(dA, a, sizeof(float) * n, cudaMemcpyHostToDevice, stream_));
+    if (b) CR_CUDA(cudaMemcpyAsync(dB, b, sizeof(float) * n, cudaMemcpyHostToDevice, stream_));
+    launchEvalMath(fn, dA, dB, dO, n, stream_);
+    launches_++;
+    CR_CUDA(cudaMemcpyAsync(out, dO, sizeof(float) * n, cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    CR_CUDA(cudaGetLastError());
+    dfree(dA); dfree(dB); dfree(dO);
+}
+
+}  // namespace cr

@@ -1,0 +1,134 @@
+// cr_renderer.h -- the single implicit renderer behind the C ABI.
+//
+// Replaces the global state + frame loop of libEyeRenderer3/libEyeRenderer.cpp:81-92,152-195,
+// 229-242 and the per-camera device buffers of cameras/CompoundEye.cpp:30-62,98-183.  Headless:
+// no GLFW/GL (the reference creates a window at load time, libEyeRenderer.cpp:88-90).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cr_device.h"
+#include "cr_scene.h"
+
+namespace cr {
+
+struct CompoundState {                 // device side of one CompoundEye camera
+    float4* dOmm = nullptr;
+    uint4* dRng = nullptr;
+    float4* dSummed = nullptr;
+    float* dSamples = nullptr;         // only for raw_ommatidial_samples
+    uint32_t* dMap = nullptr;          // cached pixel -> ommatidium map
+    int mapMode = -2, mapW = 0, mapH = 0;
+    uint64_t mapEyeVersion = 0, eyeVersion = 1;
+    int N = 0, S = 1;
+    int rngN = 0, rngS = 0;            // allocation the RNG/summed buffers were sized for
+    bool ommDirty = true;
+    bool randomsConfigured = false;    // cameras/CompoundEyeDataTypes.h:12
+    uint64_t frameIndex = 0;           // frames rendered since the streams were (re)initialised
+    uint64_t firstFrame = 0;           // frame offset applied at the next stream initialisation
+    // debug dump buffers
+    float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; size_t dumpCap = 0;
+};
+
+class Renderer {
+public:
+    Renderer();
+    ~Renderer();
+
+    void setDevice(int dev);
+    void loadScene(const std::string& path);
+    void stop();
+    void setRenderSize(int w, int h);
+    double renderFrame();
+    unsigned char* framePointer();
+    void saveFrame(const std::string& path);
+
+    HostScene& scene() { return scene_; }
+    bool hasScene() const { return loaded_; }
+    HostCamera& camera();
+    size_t cameraCount();
+    size_t cameraIndex() const { return current_; }
+    void setCurrentCamera(int index);
+    bool compoundActive();
+
+    void setSamples(int s);
+    int samples();
+    size_t ommatidialCount();
+    void setOmmatidia(const Ommatidium* omm, size_t count);
+
+    bool verbose = true;
+    bool dumpRays = false;
+    int width() const { return W_; }
+    int height() const { return H_; }
+
+    // additive API
+    void copyOmmatidialData(float* outRgb);                       // float RGB per ommatidium of the last frame
+    double renderPoseBatch(const float* poses12, size_t count, unsigned char* outRgba, void* outDevice);
+    void setFirstFrame(uint64_t k);
+    double lastTraceMs() const { return lastTraceMs_; }
+    unsigned long long launchCount() const { return launches_; }
+    double bvhBuildMs() const { return bvh_.buildMs; }
+
+    // debug / parity access
+    void debugCopyBvh(float* nodes, float* tris);
+    int debugNodeCount() const { return bvh_.nNodes; }
+    void debugCopyRngStates(uint32_t* out8);                      // [N*S][8] in reference stream-id order
+    size_t debugCopyLastRays(float* origins, float* dirs, int32_t* hits4);
+    void debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8);
+    void debugCopyProjectionMap(uint32_t* out);
+    void debugEvalMath(int fn, const float* a, const float* b, float* out, int n);
+    void ensureDevice();
+
+private:
+    void uploadScene();
+    void freeScene();
+    CompoundState& compoundState(size_t camIdx);
+    void prepareCompound(CompoundState& cs, HostCamera& cam);
+    void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose);
+    void project(CompoundState& cs, const HostCamera& cam);
+    void ensureFrame();
+    void freeCompound(CompoundState& cs);
+    static DevicePose toDevicePose(const Pose& p);
+
+    HostScene scene_;
+    bool loaded_ = false;
+    size_t current_ = 0;
+    int W_ = 400, H_ = 400;                                       // libEyeRenderer.cpp:85-86
+    int device_ = -1;
+    bool deviceReady_ = false;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t evA_ = nullptr, evB_ = nullptr;
+    int numSMs_ = 148;
+    int traceOcc_ = 8;
+
+    // device scene
+    DeviceScene dscene_;
+    BvhBuildResult bvh_;
+    float* dPositions_ = nullptr;
+    uint32_t* dIndices_ = nullptr;
+    uint4* dPrims_ = nullptr;
+    float2* dUvs_ = nullptr;
+    float4* dColors_ = nullptr;
+    MeshRec* dMeshes_ = nullptr;
+    std::vector<cudaArray_t> texArrays_;
+    std::vector<cudaTextureObject_t> texObjects_;
+
+    std::map<size_t, CompoundState> compound_;
+
+    uchar4* dFrame_ = nullptr;
+    unsigned char* hFrame_ = nullptr;                             // pinned
+    size_t frameCap_ = 0;
+    int frameW_ = 0, frameH_ = 0;
+
+    double lastTraceMs_ = 0.0;
+    unsigned long long launches_ = 0;
+};
+
+Renderer& renderer();
+
+}  // namespace cr

@@ -1,0 +1,139 @@
+/* include/libEyeRenderer.h -- C ABI of libEyeRenderer3.so (B200-native build).
+ *
+ * Drop-in boundary: the 35 extern "C" entry points of the reference's
+ * libEyeRenderer3/libEyeRenderer.h:16-67 with identical names, argument order/meaning and
+ * return conventions, so python-examples/eyeRendererHelperFunctions.py (ctypes signatures at
+ * :40-71) and the python-examples run unchanged.  Each declaration cites the reference
+ * definition it replaces (libEyeRenderer3/libEyeRenderer.cpp).  One implicit global renderer per
+ * process, not thread-safe, every call synchronous -- as in the reference.
+ *
+ * Differences that are deliberate:
+ *   - headless: loading the library creates no window/GL context (reference: libEyeRenderer.cpp:88-90);
+ *     displayFrame() is a no-op;
+ *   - C++ exceptions never cross this boundary: failures are printed to stderr as
+ *     "[PyEye] ERROR: ..." and the call returns its neutral value (0 / false / "" / NULL);
+ *   - there is no CPU fallback: rendering calls fail loudly when no CUDA device is present.
+ *
+ * Symbols prefixed cr* are ADDITIONS (never substitutes) for batch rendering, multi-GPU use and
+ * parity testing.
+ */
+#ifndef LIB_EYE_RENDERER_3_B200_H
+#define LIB_EYE_RENDERER_3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+/* libEyeRenderer.h:8-14 -- 8 floats, identical to one .eye line and to the device row */
+struct OmmatidiumPacket {
+    float posX, posY, posZ;
+    float dirX, dirY, dirZ;
+    float acceptanceAngle;
+    float focalpointOffset;
+};
+
+/* layout-identical to CUDA's float3 (the reference returns float3 by value, libEyeRenderer.h:65-66) */
+#if defined(__VECTOR_TYPES_H__)
+typedef float3 crFloat3;
+#else
+typedef struct crFloat3 { float x, y, z; } crFloat3;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- configuration / frame loop ---- */
+void setVerbosity(bool v);                      /* libEyeRenderer.cpp:211-214 */
+void loadGlTFscene(const char* filepath);       /* :215-220  ASCII .gltf, builds the BVH */
+void stop(void);                                /* :289-295  frees device state */
+void setRenderSize(int w, int h);               /* :221-228 */
+double renderFrame(void);                       /* :229-242  returns host-timed milliseconds */
+void displayFrame(void);                        /* :243-258  no-op (headless) */
+void saveFrameAs(char* ppmFilename);            /* :259-269  binary P6, top-down */
+unsigned char* getFramePointer(void);           /* :270-275  uchar4[H][W], row 0 = bottom, library-owned */
+
+/* ---- camera control ---- */
+size_t getCameraCount(void);                    /* :306-309 */
+void nextCamera(void);                          /* :310-313 */
+void previousCamera(void);                      /* :322-325 */
+size_t getCurrentCameraIndex(void);             /* :314-317 */
+const char* getCurrentCameraName(void);         /* :318-321  library-owned */
+void gotoCamera(int index);                     /* :326-329  wraps modulo the camera count */
+bool gotoCameraByName(char* name);              /* :330-340  on a miss: false, camera 0 selected */
+void setCameraPosition(float x, float y, float z);                      /* :341-344 */
+void getCameraPosition(float* x, float* y, float* z);                   /* :345-351 (float& == float*) */
+void setCameraLocalSpace(float lxx, float lxy, float lxz,               /* :352-359  x, y, z axes */
+                         float lyx, float lyy, float lyz,
+                         float lzx, float lzy, float lzz);
+void rotateCameraAround(float angle, float axisX, float axisY, float axisZ);         /* :360-363 radians */
+void rotateCameraLocallyAround(float angle, float axisX, float axisY, float axisZ);  /* :364-367 */
+void translateCamera(float x, float y, float z);                        /* :368-371 */
+void translateCameraLocally(float x, float y, float z);                 /* :372-375 */
+void resetCameraPose(void);                                             /* :376-379 */
+void setCameraPose(float posX, float posY, float posZ,                  /* :380-388 reset; rot X,Y,Z; move */
+                   float rotX, float rotY, float rotZ);
+
+/* ---- compound eye ---- */
+bool isCompoundEyeActive(void);                                         /* :393-396 */
+void setCurrentEyeSamplesPerOmmatidium(int s);                          /* :397-403 max(1,s); resets RNG streams */
+int getCurrentEyeSamplesPerOmmatidium(void);                            /* :404-411 -1 if not compound */
+void changeCurrentEyeSamplesPerOmmatidiumBy(int s);                     /* :412-418 */
+size_t getCurrentEyeOmmatidialCount(void);                              /* :419-426 0 if not compound */
+void setOmmatidia(struct OmmatidiumPacket* omms, size_t count);         /* :427-452 copied; caller keeps ownership */
+const char* getCurrentEyeDataPath(void);                                /* :453-460 "" if not compound */
+void setCurrentEyeShaderName(char* name);                               /* :461-468 projection suffix */
+
+/* ---- scene queries ---- */
+bool isInsideHitGeometry(float x, float y, float z, char* name);        /* :470-473 */
+crFloat3 getGeometryMaxBounds(char* name);                              /* :474-477 */
+crFloat3 getGeometryMinBounds(char* name);                              /* :478-481 */
+
+/* =====================  additions (not in the reference)  ===================== */
+/* Select the CUDA device (default: env CR_DEVICE, else 0). Must precede the first GPU use. */
+void crSetDevice(int device);
+/* Float RGB per ommatidium of the last compound frame (sum over samples of colour/S): 3*N floats. */
+void crGetOmmatidialData(float* outRgb);
+/* Render `count` consecutive frames of the current compound eye, one per pose.  poses: 12 floats
+ * each (position, x axis, y axis, z axis).  Output row p = the single_dimension_fast row of pose p
+ * (4 bytes per ommatidium).  outDevice (a CUDA device pointer) takes precedence over outHost.
+ * Returns host-timed milliseconds. */
+double crRenderPoseBatch(const float* poses, size_t count, unsigned char* outHost, void* outDevice);
+/* Position the RNG streams as if `frame` frames had already been rendered (pose sharding/restart);
+ * takes effect at the next stream initialisation, which this call forces. */
+void crSetFirstFrame(uint64_t frame);
+/* CUDA-event time of the last compound trace launch(es), milliseconds. */
+double crGetLastTraceMs(void);
+/* Kernels launched by this library so far. */
+unsigned long long crGetLaunchCount(void);
+/* Build time of the BVH of the loaded scene, milliseconds. */
+double crGetBvhBuildMs(void);
+
+/* ---- parity / debug access (used by tests and the roofline counters only) ---- */
+size_t crDebugGetTriangleCount(void);
+size_t crDebugGetVertexCount(void);
+size_t crDebugGetMeshCount(void);
+void crDebugCopyTriangles(float* out9);          /* host loader output: v0, e1, e2 per flattened prim */
+void crDebugCopyTriangleMesh(int32_t* out);      /* mesh group of each flattened primitive */
+void crDebugCopyMeshInfo(int32_t* out4, float* baseColor4);  /* per mesh: colorType, hasUV, texture, material */
+void crDebugCopyCornerAttributes(float* uv6, float* col12);  /* per prim: 3 x uv, 3 x rgba (either may be NULL) */
+void crDebugCopyCameraPose(float* out12);        /* current camera: position, x, y, z axes */
+void crDebugCopyCameraScale(float* out3);
+int crDebugGetCameraKind(void);                  /* 0 perspective, 1 panoramic, 2 orthographic, 3 compound */
+void crDebugCopyOmmatidia(float* out8);
+int crDebugGetMissShader(void);
+size_t crDebugGetBvhNodeCount(void);
+void crDebugCopyBvh(float* nodes16, float* tris12);
+void crDebugSetRayDump(bool on);
+size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* stream-id order N*s+o */
+void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */
+void crDebugTraceRays(const float* origins3, const float* dirs3, const float* tmins, int n, int32_t* hits8);
+void crDebugCopyProjectionMap(uint32_t* out);    /* W*H ommatidium indices of the cached map */
+void crDebugEvalMath(int fn, const float* a, const float* b, float* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

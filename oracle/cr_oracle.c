@@ -1,0 +1,909 @@
+/* oracle/cr_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("oracle") of the compound-eye render path of BrainsOnBoard/compound-ray.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (compound-ray_b200/) never does.
+ *
+ * PARITY PIN STATUS (see DESIGN.md "Oracle"):
+ *   - XORWOW RNG: pinned against NVIDIA cuRAND's own host implementation compiled from
+ *     /usr/local/cuda/include/curand_kernel.h (oracle/_ref/curand_kat, golden vectors in
+ *     tests/golden/xorwow_kat.json).
+ *   - Loader math (node transforms, camera axes): pinned against the reference's sutil headers
+ *     compiled from /root/reference (oracle/_ref/sutil_kat, golden vectors in tests/golden/).
+ *   - Traversal / hit selection: "parity unpinned" -- the reference delegates it to the closed
+ *     NVIDIA OptiX driver (shaders.cu:110-137), ships no tests or golden images
+ *      and cannot be built here (no OptiX SDK).  The oracle restates the
+ *     documented semantics (closest hit, two-sided, tmin/tmax) with Moller-Trumbore.
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * Floating point: plain IEEE binary32, one rounding per written operation (compile with
+ * -ffp-contract=off), transcendental functions from cr_math.h.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "cr_math.h"
+
+#define API __attribute__((visibility("default")))
+
+typedef struct { float x, y, z; } f3;
+static inline f3 mk3(float x, float y, float z) { f3 r = {x, y, z}; return r; }
+static inline f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline f3 mul3s(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+/* sutil/vec_math.h dot/cross/length/normalize (:520-545): plain products and sums. */
+static inline float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline f3 cross3(f3 a, f3 b)
+{ return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline float len3(f3 a) { return sqrtf(dot3(a, a)); }
+static inline f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return mul3s(v, inv); }
+
+/* =====================================================================================
+ *  1. cuRAND XORWOW  (reference call sites: libEyeRenderer3/shaders.cu:680-695;
+ *     algorithm: CUDA 12.9 curand_kernel.h:150-156 (state), :315-334 (matvec), :702-736
+ *     (skipahead / skipahead_sequence), :800-825 (init), :863-874 (draw);
+ *     curand_normal.h:70-87,313-326; curand_uniform.h:69-72,134-137)
+ *  The 2^67-spaced jump matrices that cuRAND ships as tables (curand_precalc.h) are derived
+ *  here from first principles: M_0 = T^(2^67), M_b = M_{b-1}^4 with T the one-step GF(2)
+ *  transition matrix of the five xorshift words.
+ * ===================================================================================== */
+typedef struct {
+    uint32_t d, v[5];
+    int32_t  boxmuller_flag;
+    float    boxmuller_extra;
+} xw_state;                                  /* 32 bytes */
+
+#define XW_NMAT 32
+static uint32_t g_seq[XW_NMAT][160][5];      /* skipahead_sequence matrices  */
+static uint32_t g_off[XW_NMAT][160][5];      /* skipahead (offset) matrices */
+static int g_tables_ready = 0;
+
+static inline void xw_step_v(uint32_t v[5])
+{
+    uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+static void xw_matvec(const uint32_t vin[5], uint32_t (*M)[5], uint32_t vout[5])
+{
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 32; j++)
+            if (vin[i] & (1u << j)) {
+                const uint32_t* row = M[i * 32 + j];
+                for (int k = 0; k < 5; k++) r[k] ^= row[k];
+            }
+    memcpy(vout, r, sizeof r);
+}
+static void xw_matsquare(uint32_t (*M)[5])
+{
+    static uint32_t tmp[160][5];
+    for (int b = 0; b < 160; b++) xw_matvec(M[b], M, tmp[b]);
+    memcpy(M, tmp, sizeof tmp);
+}
+API void cro_xorwow_build_tables(void)
+{
+    if (g_tables_ready) return;
+    static uint32_t T[160][5];
+    for (int b = 0; b < 160; b++) {
+        uint32_t v[5] = {0, 0, 0, 0, 0};
+        v[b / 32] = 1u << (b % 32);
+        xw_step_v(v);
+        memcpy(T[b], v, sizeof v);
+    }
+    memcpy(g_off[0], T, sizeof T);
+    for (int m = 1; m < XW_NMAT; m++) {
+        memcpy(g_off[m], g_off[m - 1], sizeof T);
+        xw_matsquare(g_off[m]); xw_matsquare(g_off[m]);
+    }
+    static uint32_t J[160][5];
+    memcpy(J, T, sizeof T);
+    for (int i = 0; i < 67; i++) xw_matsquare(J);          /* T^(2^67) */
+    memcpy(g_seq[0], J, sizeof J);
+    for (int m = 1; m < XW_NMAT; m++) {
+        memcpy(g_seq[m], g_seq[m - 1], sizeof J);
+        xw_matsquare(g_seq[m]); xw_matsquare(g_seq[m]);
+    }
+    g_tables_ready = 1;
+}
+static void xw_skip_with(uint32_t v[5], unsigned long long n, uint32_t (*tab)[160][5])
+{
+    int m = 0;
+    while (n && m < XW_NMAT) {
+        for (unsigned t = 0; t < (unsigned)(n & 3ull); t++) xw_matvec(v, tab[m], v);
+        n >>= 2; m++;
+    }
+}
+API void cro_xorwow_skipahead(xw_state* s, unsigned long long n)
+{
+    cro_xorwow_build_tables();
+    xw_skip_with(s->v, n, g_off);
+    s->d += 362437u * (uint32_t)n;
+}
+API void cro_xorwow_init(xw_state* s, unsigned long long seed, unsigned long long subsequence,
+                         unsigned long long offset)
+{
+    cro_xorwow_build_tables();
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    s->d = 6615241u + t1 + t0;
+    s->v[0] = 123456789u + t0;
+    s->v[1] = 362436069u ^ t0;
+    s->v[2] = 521288629u + t1;
+    s->v[3] = 88675123u ^ t1;
+    s->v[4] = 5783321u + t0;
+    xw_skip_with(s->v, subsequence, g_seq);
+    cro_xorwow_skipahead(s, offset);
+    s->boxmuller_flag = 0;
+    s->boxmuller_extra = 0.0f;
+}
+API uint32_t cro_xorwow_next(xw_state* s)
+{
+    xw_step_v(s->v);
+    s->d += 362437u;
+    return s->v[4] + s->d;
+}
+/* curand_uniform.h:69-72: x * 2^-32 + 2^-33, two rounded operations. */
+API float cro_xorwow_uniform(xw_state* s)
+{
+    uint32_t x = cro_xorwow_next(s);
+    return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+/* curand_normal.h:70-87,313-326: Box-Muller with cached second value. */
+API float cro_xorwow_normal(xw_state* s)
+{
+    if (s->boxmuller_flag != 1) {
+        uint32_t x = cro_xorwow_next(s);
+        uint32_t y = cro_xorwow_next(s);
+        float u = (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+        float v = (float)y * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2.0f);
+        float r = sqrtf(-2.0f * crm_logf(u));
+        float sn, cs;
+        crm_sincosf(v, &sn, &cs);
+        s->boxmuller_extra = cs * r;
+        s->boxmuller_flag = 1;
+        return sn * r;
+    }
+    s->boxmuller_flag = 0;
+    return s->boxmuller_extra;
+}
+/* number of raw draws consumed by the first k frames of one sample stream. */
+API unsigned long long cro_draws_before_frame(unsigned long long k)
+{ return 3ull * ((k + 1) / 2) + (k / 2); }
+
+/* =====================================================================================
+ *  2. Ommatidial sample rays   (libEyeRenderer3/shaders.cu:648-662, 664-709)
+ * ===================================================================================== */
+#define FWHM_SD_RATIO 2.35482004503094938202313865291f          /* shaders.cu:53 */
+
+/* shaders.cu:648-651.  `axis` is NOT re-normalised. */
+static inline f3 rotate_point(f3 p, float angle, f3 axis)
+{
+    float sn, cs;
+    crm_sincosf(angle, &sn, &cs);
+    f3 a = mul3s(p, cs);
+    f3 b = mul3s(cross3(axis, p), sn);
+    f3 c = mul3s(axis, (1.0f - cs) * dot3(axis, p));
+    return add3(add3(a, b), c);
+}
+/* shaders.cu:652-662 incl. the exact-zero test on the SUM of the components. */
+static inline f3 generate_offset_ray(float axis_angle, float splay, f3 axis)
+{
+    f3 perp = cross3(mk3(0.0f, 1.0f, 0.0f), axis);
+    if (perp.x + perp.y + perp.z == 0.0f) perp = mk3(0.0f, 0.0f, 1.0f);
+    else perp = normalize3(perp);
+    f3 splayed = rotate_point(axis, splay, perp);
+    return rotate_point(splayed, axis_angle, axis);
+}
+
+typedef struct {
+    float px, py, pz;       /* relativePosition   (cameras/CompoundEyeDataTypes.h:22-28) */
+    float dx, dy, dz;       /* relativeDirection */
+    float acceptance;       /* acceptanceAngleRadians (FWHM) */
+    float focal;            /* focalPointOffset */
+} ommatidium_t;
+
+typedef struct {            /* RaygenPosedContainer pose (GenericCameraDataTypes.h:17-42) */
+    float pos[3], ax[3], ay[3], az[3];
+} pose_t;
+
+/* One frame of ray generation for all N*S sample streams; stream id = N*s + o
+ * (shaders.cu:668-669).  states[id] persists between frames (shaders.cu:680-695);
+ * if !configured every stream is (re)initialised with curand_init(42, id, 0). */
+API void cro_generate_rays(const ommatidium_t* omm, int64_t N, int64_t S, const pose_t* pose,
+                           xw_state* states, int configured,
+                           float* origins, float* dirs, float* tmins)
+{
+    cro_xorwow_build_tables();
+    const f3 P = mk3(pose->pos[0], pose->pos[1], pose->pos[2]);
+    const f3 X = mk3(pose->ax[0], pose->ax[1], pose->ax[2]);
+    const f3 Y = mk3(pose->ay[0], pose->ay[1], pose->ay[2]);
+    const f3 Z = mk3(pose->az[0], pose->az[1], pose->az[2]);
+    #pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < N * S; id++) {
+        const int64_t o = id % N;
+        const ommatidium_t om = omm[o];
+        xw_state st;
+        if (!configured) cro_xorwow_init(&st, 42ull, (unsigned long long)id, 0ull);
+        else st = states[id];
+        const float sd = om.acceptance / FWHM_SD_RATIO;
+        const float splay = cro_xorwow_normal(&st) * sd;
+        const float axis_angle = cro_xorwow_uniform(&st) * CRM_PI;
+        states[id] = st;
+        const f3 axis = mk3(om.dx, om.dy, om.dz);
+        const f3 rd = generate_offset_ray(axis_angle, splay, axis);
+        const f3 rp = sub3(mk3(om.px, om.py, om.pz), mul3s(normalize3(axis), om.focal));
+        /* shaders.cu:704-709: ((pos + X*x) + Y*y) + Z*z ; direction ((X*x)+(Y*y))+(Z*z) */
+        const f3 org = add3(add3(add3(P, mul3s(X, rp.x)), mul3s(Y, rp.y)), mul3s(Z, rp.z));
+        const f3 dir = add3(add3(mul3s(X, rd.x), mul3s(Y, rd.y)), mul3s(Z, rd.z));
+        origins[3 * id + 0] = org.x; origins[3 * id + 1] = org.y; origins[3 * id + 2] = org.z;
+        dirs[3 * id + 0] = dir.x; dirs[3 * id + 1] = dir.y; dirs[3 * id + 2] = dir.z;
+        tmins[id] = om.focal;                                     /* shaders.cu:721 */
+    }
+}
+
+/* =====================================================================================
+ *  3. Closest-hit query (stands in for optixTrace, shaders.cu:110-137,717-723).
+ *     Two-sided, no any-hit, closest t in (tmin, tmax); ties on t resolved towards the
+ *     LOWEST flattened primitive index (documented tie policy).
+ *     Triangles arrive as (v0, e1 = v1 - v0, e2 = v2 - v0), 9 floats each.
+ * ===================================================================================== */
+static inline float fdot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline f3 fcross3(f3 a, f3 b)
+{
+    return mk3(fmaf(a.y, b.z, -(a.z * b.y)),
+               fmaf(a.z, b.x, -(a.x * b.z)),
+               fmaf(a.x, b.y, -(a.y * b.x)));
+}
+/* Moller-Trumbore. Returns 1 and (t,u,v) if tmin < t <= tlimit. */
+static inline int tri_test(const float* tri, f3 o, f3 d, float tmin, float tlimit,
+                           float* t, float* u, float* v)
+{
+    const f3 v0 = mk3(tri[0], tri[1], tri[2]);
+    const f3 e1 = mk3(tri[3], tri[4], tri[5]);
+    const f3 e2 = mk3(tri[6], tri[7], tri[8]);
+    const f3 p = fcross3(d, e2);
+    const float det = fdot3(e1, p);
+    if (!(det != 0.0f)) return 0;
+    const float inv = 1.0f / det;
+    const f3 s = sub3(o, v0);
+    const float uu = fdot3(s, p) * inv;
+    if (!(uu >= 0.0f && uu <= 1.0f)) return 0;
+    const f3 q = fcross3(s, e1);
+    const float vv = fdot3(d, q) * inv;
+    if (!(vv >= 0.0f && uu + vv <= 1.0f)) return 0;
+    const float tt = fdot3(e2, q) * inv;
+    if (!(tt > tmin && tt <= tlimit)) return 0;
+    *t = tt; *u = uu; *v = vv;
+    return 1;
+}
+
+typedef struct {
+    int32_t prim;           /* flattened primitive index, -1 = miss */
+    float t, u, v;
+} hit_t;
+
+API void cro_trace_bruteforce(const float* tris, int64_t T, const float* origins, const float* dirs,
+                              const float* tmins, int64_t R, float tmax, hit_t* hits)
+{
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t r = 0; r < R; r++) {
+        const f3 o = mk3(origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]);
+        const f3 d = mk3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        hit_t best = {-1, tmax, 0.0f, 0.0f};
+        for (int64_t i = 0; i < T; i++) {
+            float t, u, v;
+            if (tri_test(tris + 9 * i, o, d, tmins[r], best.t, &t, &u, &v)) {
+                if (t < best.t || best.prim < 0 || (int32_t)i < best.prim) {
+                    best.prim = (int32_t)i; best.t = t; best.u = u; best.v = v;
+                }
+            }
+        }
+        hits[r] = best;
+    }
+}
+
+/* ---- the oracle's own BVH (binned SAH, built on the CPU) so that million-triangle scenes
+ *      are tractable for the CPU baseline.  Results are identical to brute force because the
+ *      box test below is conservative (see slab_test). ---- */
+typedef struct {
+    float bmin[3], bmax[3];
+    int32_t left, right;        /* internal: child node indices; leaf: left = -1 */
+    int32_t start, count;       /* leaf: range in prim index array */
+} obvh_node;
+
+typedef struct {
+    obvh_node* nodes; int32_t n_nodes, cap_nodes;
+    int32_t* prims; int64_t T;
+    const float* tris;
+    float* cmin; float* cmax; float* cen;    /* per-triangle bounds and centroids */
+} obvh;
+
+static void tri_bounds(const float* t, float* mn, float* mx)
+{
+    for (int a = 0; a < 3; a++) {
+        float p0 = t[a], p1 = t[a] + t[3 + a], p2 = t[a] + t[6 + a];
+        mn[a] = fminf(p0, fminf(p1, p2));
+        mx[a] = fmaxf(p0, fmaxf(p1, p2));
+    }
+}
+static int32_t obvh_new_node(obvh* b)
+{
+    if (b->n_nodes == b->cap_nodes) {
+        b->cap_nodes = b->cap_nodes ? b->cap_nodes * 2 : 1024;
+        b->nodes = (obvh_node*)realloc(b->nodes, sizeof(obvh_node) * (size_t)b->cap_nodes);
+    }
+    return b->n_nodes++;
+}
+#define OBVH_BINS 16
+#define OBVH_LEAF 4
+static void obvh_build_rec(obvh* b, int32_t ni, int32_t start, int32_t count)
+{
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int32_t i = start; i < start + count; i++) {
+        const int32_t p = b->prims[i];
+        for (int a = 0; a < 3; a++) {
+            mn[a] = fminf(mn[a], b->cmin[3 * p + a]); mx[a] = fmaxf(mx[a], b->cmax[3 * p + a]);
+            cmn[a] = fminf(cmn[a], b->cen[3 * p + a]); cmx[a] = fmaxf(cmx[a], b->cen[3 * p + a]);
+        }
+    }
+    {
+        obvh_node* n = &b->nodes[ni];
+        memcpy(n->bmin, mn, sizeof mn); memcpy(n->bmax, mx, sizeof mx);
+        n->left = -1; n->right = -1; n->start = start; n->count = count;
+    }
+    if (count <= OBVH_LEAF) return;
+    int axis = 0;
+    float ext = cmx[0] - cmn[0];
+    for (int a = 1; a < 3; a++) if (cmx[a] - cmn[a] > ext) { ext = cmx[a] - cmn[a]; axis = a; }
+    int32_t mid = -1;
+    if (ext > 0.0f) {
+        int cnt[OBVH_BINS]; float bmn[OBVH_BINS][3], bmx[OBVH_BINS][3];
+        for (int k = 0; k < OBVH_BINS; k++) {
+            cnt[k] = 0;
+            for (int a = 0; a < 3; a++) { bmn[k][a] = INFINITY; bmx[k][a] = -INFINITY; }
+        }
+        const float scale = (float)OBVH_BINS / ext;
+        for (int32_t i = start; i < start + count; i++) {
+            const int32_t p = b->prims[i];
+            int k = (int)((b->cen[3 * p + axis] - cmn[axis]) * scale);
+            if (k >= OBVH_BINS) k = OBVH_BINS - 1;
+            if (k < 0) k = 0;
+            cnt[k]++;
+            for (int a = 0; a < 3; a++) {
+                bmn[k][a] = fminf(bmn[k][a], b->cmin[3 * p + a]);
+                bmx[k][a] = fmaxf(bmx[k][a], b->cmax[3 * p + a]);
+            }
+        }
+        float la[OBVH_BINS], ra[OBVH_BINS]; int lc[OBVH_BINS], rc[OBVH_BINS];
+        float amn[3] = {INFINITY, INFINITY, INFINITY}, amx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        int c = 0;
+        for (int k = 0; k < OBVH_BINS; k++) {
+            c += cnt[k];
+            for (int a = 0; a < 3; a++) { amn[a] = fminf(amn[a], bmn[k][a]); amx[a] = fmaxf(amx[a], bmx[k][a]); }
+            float dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
+            la[k] = c ? 2.0f * (dx * dy + dy * dz + dz * dx) : 0.0f; lc[k] = c;
+        }
+        for (int a = 0; a < 3; a++) { amn[a] = INFINITY; amx[a] = -INFINITY; }
+        c = 0;
+        for (int k = OBVH_BINS - 1; k >= 0; k--) {
+            c += cnt[k];
+            for (int a = 0; a < 3; a++) { amn[a] = fminf(amn[a], bmn[k][a]); amx[a] = fmaxf(amx[a], bmx[k][a]); }
+            float dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
+            ra[k] = c ? 2.0f * (dx * dy + dy * dz + dz * dx) : 0.0f; rc[k] = c;
+        }
+        float best = INFINITY; int bestk = -1;
+        for (int k = 0; k < OBVH_BINS - 1; k++) {
+            if (lc[k] == 0 || rc[k + 1] == 0) continue;
+            float cost = la[k] * (float)lc[k] + ra[k + 1] * (float)rc[k + 1];
+            if (cost < best) { best = cost; bestk = k; }
+        }
+        if (bestk >= 0) {
+            int32_t i = start, j = start + count - 1;
+            while (i <= j) {
+                const int32_t p = b->prims[i];
+                int k = (int)((b->cen[3 * p + axis] - cmn[axis]) * scale);
+                if (k >= OBVH_BINS) k = OBVH_BINS - 1;
+                if (k < 0) k = 0;
+                if (k <= bestk) i++;
+                else { b->prims[i] = b->prims[j]; b->prims[j] = p; j--; }
+            }
+            mid = i;
+        }
+    }
+    if (mid <= start || mid >= start + count) mid = start + count / 2;   /* fallback: halves */
+    const int32_t l = obvh_new_node(b);
+    const int32_t r = obvh_new_node(b);
+    b->nodes[ni].left = l; b->nodes[ni].right = r;
+    obvh_build_rec(b, l, start, mid - start);
+    obvh_build_rec(b, r, mid, start + count - mid);
+}
+API void* cro_bvh_build(const float* tris, int64_t T)
+{
+    obvh* b = (obvh*)calloc(1, sizeof(obvh));
+    b->T = T; b->tris = tris;
+    b->prims = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1));
+    b->cmin = (float*)malloc(sizeof(float) * 3 * (size_t)(T > 0 ? T : 1));
+    b->cmax = (float*)malloc(sizeof(float) * 3 * (size_t)(T > 0 ? T : 1));
+    b->cen = (float*)malloc(sizeof(float) * 3 * (size_t)(T > 0 ? T : 1));
+    for (int64_t i = 0; i < T; i++) {
+        b->prims[i] = (int32_t)i;
+        tri_bounds(tris + 9 * i, b->cmin + 3 * i, b->cmax + 3 * i);
+        for (int a = 0; a < 3; a++) b->cen[3 * i + a] = 0.5f * (b->cmin[3 * i + a] + b->cmax[3 * i + a]);
+    }
+    if (T > 0) { obvh_new_node(b); obvh_build_rec(b, 0, 0, (int32_t)T); }
+    free(b->cmin); free(b->cmax); free(b->cen); b->cmin = b->cmax = b->cen = NULL;
+    return b;
+}
+API void cro_bvh_free(void* h)
+{
+    obvh* b = (obvh*)h;
+    if (!b) return;
+    free(b->nodes); free(b->prims); free(b);
+}
+/* Conservative slab test: entry/exit distances are widened by a few ulps so that a hit the
+ * triangle test accepts is never culled by box rounding; returns entry distance. */
+static inline int slab_test(const float* bmin, const float* bmax, f3 o, f3 inv, float tmin, float tlimit,
+                            float* tenter)
+{
+    float t0 = (bmin[0] - o.x) * inv.x, t1 = (bmax[0] - o.x) * inv.x;
+    float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+    t0 = (bmin[1] - o.y) * inv.y; t1 = (bmax[1] - o.y) * inv.y;
+    lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+    t0 = (bmin[2] - o.z) * inv.z; t1 = (bmax[2] - o.z) * inv.z;
+    lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+    /* widen: relative 4 ulp plus a tiny absolute term */
+    const float eps = 4.0f * 1.1920929e-7f;
+    lo = lo - (fabsf(lo) * eps + 1e-30f);
+    hi = hi + (fabsf(hi) * eps + 1e-30f);
+    lo = fmaxf(lo, tmin); hi = fminf(hi, tlimit);
+    *tenter = lo;
+    return lo <= hi;
+}
+static inline f3 safe_inv_dir(f3 d)
+{
+    /* exact IEEE reciprocal; zero components give +-inf which the min/max slab handles
+     * except for 0*inf = NaN (origin exactly on a slab plane) -- fminf/fmaxf drop NaN. */
+    return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+}
+API void cro_trace_bvh(void* h, const float* origins, const float* dirs, const float* tmins, int64_t R,
+                       float tmax, hit_t* hits, int64_t* counters /* [2]: nodes, tris ; may be NULL */)
+{
+    const obvh* b = (const obvh*)h;
+    int64_t tot_nodes = 0, tot_tris = 0;
+    #pragma omp parallel for schedule(dynamic, 256) reduction(+:tot_nodes, tot_tris)
+    for (int64_t r = 0; r < R; r++) {
+        const f3 o = mk3(origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]);
+        const f3 d = mk3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        const f3 inv = safe_inv_dir(d);
+        hit_t best = {-1, tmax, 0.0f, 0.0f};
+        if (b->n_nodes > 0) {
+            int32_t stack[128]; int sp = 0;
+            stack[sp++] = 0;
+            while (sp) {
+                const obvh_node* n = &b->nodes[stack[--sp]];
+                float te;
+                tot_nodes++;
+                if (!slab_test(n->bmin, n->bmax, o, inv, tmins[r], best.t, &te)) continue;
+                if (n->left < 0) {
+                    for (int32_t i = n->start; i < n->start + n->count; i++) {
+                        const int32_t p = b->prims[i];
+                        float t, u, v;
+                        tot_tris++;
+                        if (tri_test(b->tris + 9 * (int64_t)p, o, d, tmins[r], best.t, &t, &u, &v)) {
+                            if (t < best.t || best.prim < 0 || p < best.prim) {
+                                best.prim = p; best.t = t; best.u = u; best.v = v;
+                            }
+                        }
+                    }
+                } else {
+                    /* near child first (by box centre along the dominant split is unknown here:
+                     * use entry distance) */
+                    float tl, tr;
+                    const obvh_node* L = &b->nodes[n->left];
+                    const obvh_node* Rn = &b->nodes[n->right];
+                    int hl = slab_test(L->bmin, L->bmax, o, inv, tmins[r], best.t, &tl);
+                    int hr = slab_test(Rn->bmin, Rn->bmax, o, inv, tmins[r], best.t, &tr);
+                    if (hl && hr) {
+                        if (tl <= tr) { stack[sp++] = n->right; stack[sp++] = n->left; }
+                        else          { stack[sp++] = n->left;  stack[sp++] = n->right; }
+                    } else if (hl) stack[sp++] = n->left;
+                    else if (hr) stack[sp++] = n->right;
+                }
+            }
+        }
+        hits[r] = best;
+    }
+    if (counters) { counters[0] = tot_nodes; counters[1] = tot_tris; }
+}
+
+/* Instrumented traversal of the PRODUCT's device BVH (downloaded by the test/bench through the
+ * library's crDebug* calls) so that the roofline's bytes/ray are counted on the identical
+ * tree.  Node = 16 floats:
+ *   [0..3]  = c0.min.x c0.max.x c0.min.y c0.max.y
+ *   [4..7]  = c1.min.x c1.max.x c1.min.y c1.max.y
+ *   [8..11] = c0.min.z c0.max.z c1.min.z c1.max.z
+ *   [12],[13] = child refs as int bits: >= 0 internal node index; < 0 leaf with x = ~ref,
+ *               first triangle = x >> 3 (position in the sorted array), count = (x & 7) + 1
+ * Triangle = 12 floats: v0.xyz, prim(int bits), e1.xyz, pad, e2.xyz, pad.
+ * Visiting order: near child first (smaller entry distance; ties -> child 0 first). */
+API void cro_trace_device_bvh(const float* nodes, int64_t n_nodes, const float* dtris, int64_t T,
+                              const float* origins, const float* dirs, const float* tmins, int64_t R,
+                              float tmax, hit_t* hits, int64_t* counters)
+{
+    int64_t tot_nodes = 0, tot_tris = 0;
+    (void)n_nodes; (void)T;
+    #pragma omp parallel for schedule(dynamic, 256) reduction(+:tot_nodes, tot_tris)
+    for (int64_t r = 0; r < R; r++) {
+        const f3 o = mk3(origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]);
+        const f3 d = mk3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        const f3 inv = safe_inv_dir(d);
+        hit_t best = {-1, tmax, 0.0f, 0.0f};
+        int32_t stack[256]; int sp = 0;
+        if (n_nodes > 0) stack[sp++] = 0;
+        while (sp) {
+            const int32_t ref = stack[--sp];
+            if (ref < 0) {
+                const int32_t first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
+                for (int32_t i = first; i < first + cnt; i++) {
+                    const float* tp = dtris + 12 * (int64_t)i;
+                    float tri[9] = {tp[0], tp[1], tp[2], tp[4], tp[5], tp[6], tp[8], tp[9], tp[10]};
+                    const int32_t p = (int32_t)crm_f2u(tp[3]);
+                    float t, u, v;
+                    tot_tris++;
+                    if (tri_test(tri, o, d, tmins[r], best.t, &t, &u, &v)) {
+                        if (t < best.t || best.prim < 0 || p < best.prim) {
+                            best.prim = p; best.t = t; best.u = u; best.v = v;
+                        }
+                    }
+                }
+                continue;
+            }
+            const float* n = nodes + 16 * (int64_t)ref;
+            tot_nodes++;
+            const float b0min[3] = {n[0], n[2], n[8]}, b0max[3] = {n[1], n[3], n[9]};
+            const float b1min[3] = {n[4], n[6], n[10]}, b1max[3] = {n[5], n[7], n[11]};
+            float t0, t1;
+            const int h0 = slab_test(b0min, b0max, o, inv, tmins[r], best.t, &t0);
+            const int h1 = slab_test(b1min, b1max, o, inv, tmins[r], best.t, &t1);
+            const int32_t c0 = (int32_t)crm_f2u(n[12]), c1 = (int32_t)crm_f2u(n[13]);
+            if (h0 && h1) {
+                if (t0 <= t1) { stack[sp++] = c1; stack[sp++] = c0; }
+                else          { stack[sp++] = c0; stack[sp++] = c1; }
+            } else if (h0) stack[sp++] = c0;
+            else if (h1)   stack[sp++] = c1;
+        }
+        hits[r] = best;
+    }
+    if (counters) { counters[0] = tot_nodes; counters[1] = tot_tris; }
+}
+
+/* =====================================================================================
+ *  4. Shading  (closest hit: shaders.cu:779-811 live part; cuda/LocalGeometry.h:55-156;
+ *     miss: shaders.cu:740-756)
+ * ===================================================================================== */
+typedef struct {
+    int32_t color_type;     /* -1 none, else glTF component type of COLOR_0 (5126/5123/5121) */
+    int32_t has_uv;         /* TEXCOORD_0 present */
+    int32_t tex;            /* base colour texture index or -1 */
+    float base_color[4];    /* material baseColorFactor (default 1,1,1,1) */
+} mesh_info;
+
+typedef struct {
+    int32_t width, height;
+    const uint8_t* rgba;    /* width*height*4, row 0 first, as decoded by stb (4 components) */
+} texture_t;
+
+typedef struct {
+    int64_t T;
+    const float* tris;          /* [T][9]  v0,e1,e2 (world space) */
+    const int32_t* tri_mesh;    /* [T] mesh (primitive group) index */
+    const float* corner_uv;     /* [T][3][2] or NULL */
+    const float* corner_col;    /* [T][3][4] (already scaled to float) or NULL */
+    const mesh_info* meshes; int32_t n_meshes;
+    const texture_t* textures; int32_t n_textures;
+    int32_t miss_shader;        /* 0 = default_background, 1 = simple_sky */
+    int32_t tex_frac_bits;      /* bilinear weight quantisation, 8 = CUDA texture unit (1.8 fixed point); 0 = none */
+} scene_t;
+
+static inline float texel_ch(const texture_t* tx, int x, int y, int ch)
+{ return (float)tx->rgba[((size_t)y * (size_t)tx->width + (size_t)x) * 4 + (size_t)ch] / 255.0f; }
+
+/* cudaAddressModeWrap + cudaFilterModeLinear + normalized coords + cudaReadModeNormalizedFloat
+ * (the only sampler the reference can create: MulticamScene.cpp:801-834).  CUDA Programming
+ * Guide "Texture Fetching / Linear Filtering": xB = N*frac(x) - 0.5, i = floor(xB),
+ * alpha = frac(xB) stored in 9-bit fixed point with 8 fractional bits. */
+static void tex2d_wrap_linear(const texture_t* tx, float u, float v, int frac_bits, float out[3])
+{
+    const int W = tx->width, H = tx->height;
+    float fu = u - floorf(u), fv = v - floorf(v);
+    float xb = fu * (float)W - 0.5f, yb = fv * (float)H - 0.5f;
+    float xf = floorf(xb), yf = floorf(yb);
+    float a = xb - xf, b = yb - yf;
+    if (frac_bits > 0) {
+        const float q = (float)(1 << frac_bits);
+        a = floorf(a * q + 0.5f) / q;
+        b = floorf(b * q + 0.5f) / q;
+    }
+    int x0 = (int)xf, y0 = (int)yf;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = ((x0 % W) + W) % W; x1 = ((x1 % W) + W) % W;
+    y0 = ((y0 % H) + H) % H; y1 = ((y1 % H) + H) % H;
+    for (int ch = 0; ch < 3; ch++) {
+        float t00 = texel_ch(tx, x0, y0, ch), t10 = texel_ch(tx, x1, y0, ch);
+        float t01 = texel_ch(tx, x0, y1, ch), t11 = texel_ch(tx, x1, y1, ch);
+        out[ch] = (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+    }
+}
+
+static inline f3 linearize(f3 c)            /* shaders.cu:100-107 */
+{ return mk3(crm_powf(c.x, 2.2f), crm_powf(c.y, 2.2f), crm_powf(c.z, 2.2f)); }
+
+static f3 shade_hit(const scene_t* sc, const hit_t* h)
+{
+    const int32_t m = sc->tri_mesh[h->prim];
+    const mesh_info* mi = &sc->meshes[m];
+    const float w0 = 1.0f - h->u - h->v;
+    if (mi->color_type != -1 && sc->corner_col) {              /* LocalGeometry.h:107-150 */
+        const float* c = sc->corner_col + 12 * (int64_t)h->prim;
+        f3 col;
+        col.x = w0 * c[0] + h->u * c[4] + h->v * c[8];
+        col.y = w0 * c[1] + h->u * c[5] + h->v * c[9];
+        col.z = w0 * c[2] + h->u * c[6] + h->v * c[10];
+        return linearize(col);                                  /* shaders.cu:790-797 */
+    }
+    if (mi->tex >= 0 && mi->tex < sc->n_textures) {            /* shaders.cu:801-805 */
+        float uu, vv;
+        if (mi->has_uv && sc->corner_uv) {                     /* LocalGeometry.h:89-96 */
+            const float* t = sc->corner_uv + 6 * (int64_t)h->prim;
+            uu = w0 * t[0] + h->u * t[2] + h->v * t[4];
+            vv = w0 * t[1] + h->u * t[3] + h->v * t[5];
+        } else { uu = h->u; vv = h->v; }                       /* LocalGeometry.h:97-103 */
+        float tx[3];
+        tex2d_wrap_linear(&sc->textures[mi->tex], uu, vv, sc->tex_frac_bits, tx);
+        return linearize(mk3(tx[0], tx[1], tx[2]));
+    }
+    return mk3(mi->base_color[0], mi->base_color[1], mi->base_color[2]);   /* shaders.cu:785 */
+}
+
+static f3 shade_miss(int shader, f3 raydir)
+{
+    const f3 dir = normalize3(raydir);
+    if (shader == 1) {                                          /* __miss__simple_sky :749-756 */
+        const float mix = fminf(fmaxf(0.0f, (crm_asinf(dir.y) * 2.0f) / CRM_PI), 1.0f);
+        /* sutil float3/float = multiply by the rounded reciprocal (sutil/vec_math.h:479-483) */
+        const float i255 = 1.0f / 255.0f;
+        const f3 upper = mk3(1.0f * i255, 31.0f * i255, 117.0f * i255);
+        const f3 lower = mk3((143.0f * i255) * 0.8f, (179.0f * i255) * 0.8f, (203.0f * i255) * 0.8f);
+        return add3(mul3s(lower, 1.0f - mix), mul3s(upper, mix));
+    }
+    /* __miss__default_background :740-747 */
+    const float border = 0.01f;
+    if (fabsf(dir.x) < border || fabsf(dir.y) < border || fabsf(dir.z) < border) return mk3(0.0f, 0.0f, 0.0f);
+    return mk3((crm_atan2f(dir.z, dir.x) + CRM_PI) / (CRM_PI * 2.0f),
+               (crm_asinf(dir.y) + CRM_PI / 2.0f) / CRM_PI, 0.0f);
+}
+
+API void cro_shade(const scene_t* sc, const hit_t* hits, const float* dirs, int64_t R, float* rgb)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < R; r++) {
+        f3 c;
+        if (hits[r].prim >= 0) c = shade_hit(sc, &hits[r]);
+        else c = shade_miss(sc->miss_shader, mk3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]));
+        rgb[3 * r] = c.x; rgb[3 * r + 1] = c.y; rgb[3 * r + 2] = c.z;
+    }
+}
+
+/* compound buffer: sample/S at [N*s+o] (shaders.cu:730), then the projection pass sums
+ * s = 0..S-1 sequentially in fp32 (shaders.cu:341-347). */
+API void cro_accumulate(const float* rgb, int64_t N, int64_t S, float* compound /* [S*N][3] */,
+                        float* summed /* [N][3] */)
+{
+    const float inv = 1.0f / (float)(uint32_t)S;
+    for (int64_t id = 0; id < N * S; id++)
+        for (int c = 0; c < 3; c++) compound[3 * id + c] = rgb[3 * id + c] * inv;
+    for (int64_t o = 0; o < N; o++)
+        for (int c = 0; c < 3; c++) {
+            float sum = 0.0f;
+            for (int64_t s = 0; s < S; s++) sum += compound[3 * (N * s + o) + c];
+            summed[3 * o + c] = sum;
+        }
+}
+
+/* =====================================================================================
+ *  5. Output encoding and projection  (shaders.cu:180-189, 354-640)
+ * ===================================================================================== */
+static inline float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+API void cro_make_color(const float* c, uint8_t* out)          /* shaders.cu:180-189 */
+{
+    const float gamma = 2.2f;
+    const float ex = (float)(1.0 / (double)gamma);              /* `1.0/gamma` is a double expr */
+    out[0] = (uint8_t)(crm_powf(clamp01(c[0]), ex) * 255.0f);
+    out[1] = (uint8_t)(crm_powf(clamp01(c[1]), ex) * 255.0f);
+    out[2] = (uint8_t)(crm_powf(clamp01(c[2]), ex) * 255.0f);
+    out[3] = 255u;
+}
+
+enum {
+    PROJ_RAW_SAMPLES = 0, PROJ_SINGLE_DIM = 1, PROJ_SINGLE_DIM_FAST = 2,
+    PROJ_SPH_POSITIONWISE = 3, PROJ_SPH_ORIENTATIONWISE = 4, PROJ_SPH_SPLIT_ORIENTATIONWISE = 5,
+    PROJ_SPH_ORIENTATIONWISE_IDS = 6, PROJ_SPH_POSITIONWISE_IDS = 7
+};
+
+/* nearest-ommatidium search of the spherical modes (shaders.cu:412-448, 454-490, 496-541,
+ * 548-593, 600-640): first index minimising acos(dot/(|a||v|)), strict '<', NaN never wins. */
+static uint32_t nearest_ommatidium(const ommatidium_t* omm, int64_t N, int mode, int W, int H, int x, int y)
+{
+    float dx, dy, uvx;
+    uvx = (float)x / (float)W;
+    if (mode == PROJ_SPH_SPLIT_ORIENTATIONWISE) {               /* :505-513 */
+        float sx = uvx * 2.0f, sy = ((float)y / (float)H) * 1.0f;
+        float sub = sx > 1.0f ? 1.0f : 0.0f;
+        float mx = sx - sub;
+        /* `modded*2.0 - 1.0f`: float2 * double -> sutil has float2*float only, the literal
+         * converts to float */
+        dx = mx * 2.0f - 1.0f; dy = sy * 2.0f - 1.0f;
+    } else {
+        dx = 2.0f * uvx - 1.0f; dy = 2.0f * ((float)y / (float)H) - 1.0f;
+    }
+    const float ax = dx * (-CRM_PI) + CRM_PI / 2.0f;
+    const float ay = dy * (CRM_PI / 2.0f) + 0.0f;
+    float sx_, cx_, sy_, cy_;
+    crm_sincosf(ax, &sx_, &cx_);
+    crm_sincosf(ay, &sy_, &cy_);
+    const f3 usp = mk3(cx_ * cy_, sy_, sx_ * cy_);
+    const int by_pos = (mode == PROJ_SPH_POSITIONWISE || mode == PROJ_SPH_POSITIONWISE_IDS);
+    const float lu = len3(usp);
+    uint32_t closest = 0;
+    float smallest = 0.0f;
+    for (int64_t i = 0; i < N; i++) {
+        const f3 a = by_pos ? mk3(omm[i].px, omm[i].py, omm[i].pz) : mk3(omm[i].dx, omm[i].dy, omm[i].dz);
+        const float ang = crm_acosf(dot3(a, usp) / (len3(a) * lu));
+        if (i == 0) { smallest = ang; continue; }
+        int eligible = 1;
+        if (mode == PROJ_SPH_SPLIT_ORIENTATIONWISE)
+            eligible = ((omm[i].px > 0.0f && uvx > 0.5f) || (omm[i].px < 0.0f && uvx < 0.5f));
+        if (eligible && ang < smallest) { smallest = ang; closest = (uint32_t)i; }
+    }
+    return closest;
+}
+
+API void cro_projection_map(const ommatidium_t* omm, int64_t N, int mode, int W, int H, uint32_t* map)
+{
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < (int64_t)W * H; p++)
+        map[p] = nearest_ommatidium(omm, N, mode, W, H, (int)(p % W), (int)(p / W));
+}
+
+/* Full projection pass into a W x H uchar4 frame (row 0 = bottom row as in the reference).
+ * `frame` is updated in place: modes that do not touch a pixel leave it as it was. */
+API void cro_project(const ommatidium_t* omm, int64_t N, int64_t S, int mode, int W, int H,
+                     const float* compound /* [S*N][3] */, uint8_t* frame /* [H][W][4] */)
+{
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < (int64_t)W * H; p++) {
+        const int x = (int)(p % W), y = (int)(p / W);
+        uint8_t* px = frame + 4 * p;
+        float sum[3];
+        uint32_t idx;
+        switch (mode) {
+        case PROJ_RAW_SAMPLES:                                  /* :354-369 */
+            if (y >= S || x >= N) break;
+            cro_make_color(compound + 3 * (N * (int64_t)y + x), px);
+            break;
+        case PROJ_SINGLE_DIM_FAST:                              /* :396-406 */
+            if (y > 0 || x >= N) break;
+            /* fallthrough to summation with idx = x */
+            __attribute__((fallthrough));
+        case PROJ_SINGLE_DIM:                                   /* :375-390 */
+            idx = (mode == PROJ_SINGLE_DIM) ? (uint32_t)(((uint64_t)(uint32_t)x * (uint64_t)N) / (uint64_t)(uint32_t)W)
+                                            : (uint32_t)x;
+            for (int c = 0; c < 3; c++) {
+                float s_ = 0.0f;
+                for (int64_t s = 0; s < S; s++) s_ += compound[3 * (N * s + idx) + c];
+                sum[c] = s_;
+            }
+            cro_make_color(sum, px);
+            break;
+        case PROJ_SPH_ORIENTATIONWISE_IDS: case PROJ_SPH_POSITIONWISE_IDS:   /* :583-592 */
+            idx = nearest_ommatidium(omm, N, mode, W, H, x, y);
+            px[0] = (uint8_t)(idx >> 24); px[1] = (uint8_t)((idx >> 16) & 0xff);
+            px[2] = (uint8_t)((idx >> 8) & 0xff); px[3] = (uint8_t)(idx & 0xff);
+            break;
+        default:
+            idx = nearest_ommatidium(omm, N, mode, W, H, x, y);
+            for (int c = 0; c < 3; c++) {
+                float s_ = 0.0f;
+                for (int64_t s = 0; s < S; s++) s_ += compound[3 * (N * s + idx) + c];
+                sum[c] = s_;
+            }
+            cro_make_color(sum, px);
+            break;
+        }
+    }
+}
+
+/* =====================================================================================
+ *  6. Ordinary cameras (shaders.cu:198-333): one primary ray per pixel, tmin 0.01.
+ *     kind: 0 pinhole (scale xyz), 1 panoramic (scale.x = startRadius), 2 orthographic (scale xy)
+ * ===================================================================================== */
+API void cro_camera_rays(int kind, const pose_t* pose, const float* scale, int W, int H,
+                         float* origins, float* dirs, float* tmins)
+{
+    const f3 P = mk3(pose->pos[0], pose->pos[1], pose->pos[2]);
+    const f3 X = mk3(pose->ax[0], pose->ax[1], pose->ax[2]);
+    const f3 Y = mk3(pose->ay[0], pose->ay[1], pose->ay[2]);
+    const f3 Z = mk3(pose->az[0], pose->az[1], pose->az[2]);
+    for (int64_t p = 0; p < (int64_t)W * H; p++) {
+        const int x = (int)(p % W), y = (int)(p / W);
+        const float dx = 2.0f * (((float)x + 0.0f) / (float)W) - 1.0f;
+        const float dy = 2.0f * (((float)y + 0.0f) / (float)H) - 1.0f;
+        f3 o, d;
+        if (kind == 0) {            /* :198-239  dir = Z*sz + dx*X*sx + dy*Y*sy */
+            d = add3(add3(mul3s(Z, scale[2]), mul3s(mul3s(X, dx), scale[0])), mul3s(mul3s(Y, dy), scale[1]));
+            o = P;
+        } else if (kind == 1) {     /* :241-285 */
+            const float ax = dx * (-CRM_PI) + CRM_PI / 2.0f, ay = dy * (CRM_PI / 2.0f) + 0.0f;
+            float sx_, cx_, sy_, cy_;
+            crm_sincosf(ax, &sx_, &cx_); crm_sincosf(ay, &sy_, &cy_);
+            const f3 od = mk3(cx_ * cy_, sy_, sx_ * cy_);
+            d = normalize3(add3(add3(mul3s(X, od.x), mul3s(Y, od.y)), mul3s(Z, od.z)));
+            o = add3(P, mul3s(d, scale[0]));
+        } else {                    /* :287-333 */
+            d = Z;
+            o = add3(add3(P, mul3s(mul3s(X, dx), scale[0])), mul3s(mul3s(Y, dy), scale[1]));
+        }
+        origins[3 * p] = o.x; origins[3 * p + 1] = o.y; origins[3 * p + 2] = o.z;
+        dirs[3 * p] = d.x; dirs[3 * p + 1] = d.y; dirs[3 * p + 2] = d.z;
+        tmins[p] = 0.01f;
+    }
+}
+
+/* =====================================================================================
+ *  7. Host-side pose arithmetic (cameras/DataRecordCamera.h:66-87; libEyeRenderer.cpp:380-388)
+ * ===================================================================================== */
+API void cro_pose_rotate_around(pose_t* p, float angle, const float* axis3)
+{
+    const f3 na = normalize3(mk3(axis3[0], axis3[1], axis3[2]));
+    float* axes[3] = {p->ax, p->ay, p->az};
+    for (int i = 0; i < 3; i++) {
+        const f3 pt = mk3(axes[i][0], axes[i][1], axes[i][2]);
+        const f3 r = rotate_point(pt, angle, na);
+        axes[i][0] = r.x; axes[i][1] = r.y; axes[i][2] = r.z;
+    }
+}
+
+/* exposed scalar math for the accuracy tests */
+API float cro_sinf(float x) { return crm_sinf(x); }
+API float cro_cosf(float x) { return crm_cosf(x); }
+API float cro_logf(float x) { return crm_logf(x); }
+API float cro_expf(float x) { return crm_expf(x); }
+API float cro_powf(float x, float y) { return crm_powf(x, y); }
+API float cro_asinf(float x) { return crm_asinf(x); }
+API float cro_acosf(float x) { return crm_acosf(x); }
+API float cro_atan2f(float y, float x) { return crm_atan2f(y, x); }
+API int cro_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+API void cro_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
