@@ -29,7 +29,7 @@ def ref_data():
     if not os.path.exists(stamp) or os.path.getmtime(stamp) < os.path.getmtime(arc):
         os.makedirs(DATA_DIR, exist_ok=True)
         with tarfile.open(arc) as tar:
-            tar.extractall(DATA_DIR)
+            tar.extractall(DATA_DIR, filter="data")
         open(stamp, "w").close()
     return DATA_DIR
 
