@@ -16,10 +16,11 @@
 //   meshes  MeshRec[nMeshes]
 // Compound eye (per camera):
 //   omm     float4[2*N]        the 32-byte ommatidium rows as loaded
+//   pre     float4[3*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp)
 //   rng     uint4[2*N*S]       32 B compact XORWOW state per sample stream, laid out [o][s]
 //             r[0] = (d, v0, v1, v2)   r[1] = (v3, v4, boxmuller_flag, boxmuller_extra bits)
-//   summed  float4[N]          per-ommatidium RGB (sum over samples of colour/S)
-//   samples float[3*S*N]       optional, reference layout [N*s+o] (raw_ommatidial_samples only)
+//   samples float[3*N*S]       per-sample colour/S, laid out [o][s] (12 B per ray, written by K1)
+//   summed  float4[N]          per-ommatidium RGB: sequential sum of the samples (K1b)
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -55,24 +56,20 @@ struct DevicePose {
 };
 
 struct EyeParams {
-    const float4* omm = nullptr;
+    const float4* pre = nullptr;  // 3 float4 per ommatidium (k_prepOmmatidia)
     uint4* rng = nullptr;
     float4* summed = nullptr;
-    float* samples = nullptr;
+    float* samples = nullptr;     // [o][s][3] per-sample colour/S
     // optional per-ray dump (debug / parity): reference stream-id order [N*s+o]
     float* dumpOrigins = nullptr;
     float* dumpDirs = nullptr;
     int4* dumpHits = nullptr;     // (prim, t bits, u bits, v bits)
     int N = 0;
     int S = 0;
-    int tileOmm = 1;              // ommatidia per CTA tile
-    int chunk = 1;                // samples per chunk (<= kTileRays)
-    int nTiles = 0;
     DevicePose pose;
 };
 
 constexpr int kTraceThreads = 128;
-constexpr int kTileRays = 512;
 constexpr float kTMax = 1e16f;
 
 struct BvhBuildResult {
@@ -97,6 +94,7 @@ enum Projection : int {
 
 // kernel launchers (cr_kernels.cu)
 void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cudaStream_t stream);
+void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream);
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);
 void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);

@@ -6,8 +6,10 @@
 // checker reproduces rays, hits and pixel maps bit for bit (see cr_math.h).
 //
 // K0  k_rngInit            curand_init(42, id, 0) per sample stream   (shaders.cu:680-685)
-// K1  k_traceCompound      raygen + BVH traversal + shading + exact-order per-ommatidium sum
-//                          (shaders.cu:664-731 + 110-137 + 740-811 + 341-347)
+//     k_prepOmmatidia      per-ommatidium invariants of the sample-ray construction
+// K1  k_traceCompound      raygen + BVH traversal + shading, one sample ray per lane
+//                          (shaders.cu:664-731 + 110-137 + 740-811)
+// K1b k_sumSamples         exact-order per-ommatidium sum (shaders.cu:341-347)
 // K2  k_projectVector/Raw  single_dimension[_fast], raw_ommatidial_samples (shaders.cu:354-406)
 // K3  k_buildProjectionMap nearest-ommatidium map of the spherical modes, cached per eye/size
 //     k_projectMap         map lookup + make_color, or ids                (shaders.cu:412-640)
@@ -130,32 +132,45 @@ __device__ __forceinline__ V3 rotatePoint(V3 p, float angle, V3 axis)   // axis 
     const V3 c = vmuls(axis, (1.0f - cs) * vdot(axis, p));
     return vadd(vadd(a, b), c);
 }
-__device__ __forceinline__ V3 generateOffsetRay(float axisAngle, float splay, V3 axis)
-{
-    V3 perp = vcross(mk(0.0f, 1.0f, 0.0f), axis);
-    if (perp.x + perp.y + perp.z == 0.0f) perp = mk(0.0f, 0.0f, 1.0f);   // exact-zero test on the SUM (:656)
-    else perp = vnormalize(perp);
-    const V3 splayed = rotatePoint(axis, splay, perp);
-    return rotatePoint(splayed, axisAngle, axis);
-}
-
 struct Ray { V3 o, d; float tmin; };
 
-__device__ __forceinline__ Ray ommatidialRay(const float4 q0, const float4 q1, const DevicePose& P, Rng& rng)
+// Per-ommatidium invariants of the sample-ray construction, hoisted out of the per-sample path
+// (identical operations in identical order, so the rays are bit-identical to evaluating
+// shaders.cu:652-709 per sample):
+//   pre[0] = (relPos - normalize(axis)*focal, sd = acceptance / FWHM_SD_RATIO)
+//   pre[1] = (axis, focal)          pre[2] = (perp, 0)
+__global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* __restrict__ pre)
 {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    const float4 q0 = omm[2 * o], q1 = omm[2 * o + 1];
     const V3 relPos = mk(q0.x, q0.y, q0.z);
     const V3 axis = mk(q0.w, q1.x, q1.y);
     const float acceptance = q1.z, focal = q1.w;
     const float sd = acceptance / CR_FWHM_SD_RATIO;
-    const float splay = rngNormal(rng) * sd;
-    const float axisAngle = rngUniform(rng) * crm::kPi;
-    const V3 rd = generateOffsetRay(axisAngle, splay, axis);
+    V3 perp = vcross(mk(0.0f, 1.0f, 0.0f), axis);
+    if (perp.x + perp.y + perp.z == 0.0f) perp = mk(0.0f, 0.0f, 1.0f);   // exact-zero test on the SUM (:656)
+    else perp = vnormalize(perp);
     const V3 rp = vsub(relPos, vmuls(vnormalize(axis), focal));
+    pre[3 * o + 0] = make_float4(rp.x, rp.y, rp.z, sd);
+    pre[3 * o + 1] = make_float4(axis.x, axis.y, axis.z, focal);
+    pre[3 * o + 2] = make_float4(perp.x, perp.y, perp.z, 0.0f);
+}
+
+__device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const DevicePose& P, Rng& rng)
+{
+    const V3 rp = mk(p0.x, p0.y, p0.z);
+    const V3 axis = mk(p1.x, p1.y, p1.z);
+    const V3 perp = mk(p2.x, p2.y, p2.z);
+    const float splay = rngNormal(rng) * p0.w;
+    const float axisAngle = rngUniform(rng) * crm::kPi;
+    const V3 splayed = rotatePoint(axis, splay, perp);
+    const V3 rd = rotatePoint(splayed, axisAngle, axis);
     const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
     Ray r;
     r.o = vadd(vadd(vadd(mk(P.px, P.py, P.pz), vmuls(X, rp.x)), vmuls(Y, rp.y)), vmuls(Z, rp.z));
     r.d = vadd(vadd(vmuls(X, rd.x), vmuls(Y, rd.y)), vmuls(Z, rd.z));
-    r.tmin = focal;                                                   // shaders.cu:721
+    r.tmin = p1.w;                                                    // shaders.cu:721
     return r;
 }
 
@@ -165,8 +180,9 @@ __device__ __forceinline__ Ray ommatidialRay(const float4 q0, const float4 q1, c
 // depend on traversal order.
 //
 // Box test: t = b*inv - o*inv as ONE fma per plane.  Conservative by construction:
-//   invN = inv*(1-2^-21), invF = inv*(1+2^-21)  absorb the rounding of 1/d and of the fma (both
-//          relative to |t|) for planes in front of the origin;
+//   inv  = rcp.approx(d) (<= 1 ulp error; only the box test uses it, never the triangle test)
+//   invN = inv*(1-2^-21), invF = inv*(1+2^-21)  absorb the error of inv and the rounding of the fma
+//          (both relative to |t|) for planes in front of the origin;
 //   addN = -(o*invN) - E, addF = -(o*invF) + E with E = 2^-21*|o*inv| absorb the rounding of the
 //          o*inv product (which is NOT relative to t).
 // Leaf boxes are additionally padded at build time (cr_bvh.cu) for the inexactness of the
@@ -182,10 +198,29 @@ struct RayBox {
     bool sx, sy, sz;          // direction negative -> near plane is max
 };
 
+__device__ __forceinline__ float rcpApprox(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)      // FMNMX3 on sm_100a
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 __device__ __forceinline__ void setupAxis(float o, float d, float& invN, float& invF, float& addN, float& addF, bool& neg)
 {
     const float dc = (fabsf(d) < 1e-18f) ? copysignf(1e-18f, d) : d;
-    const float inv = 1.0f / dc;
+    const float inv = rcpApprox(dc);
     neg = inv < 0.0f;
     invN = inv * (1.0f - 4.76837158203125e-07f);
     invF = inv * (1.0f + 4.76837158203125e-07f);
@@ -203,7 +238,7 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
     const V3 p = fcross(d, e2);
     const float det = fdot(e1, p);
     if (!(det != 0.0f)) return false;
-    const float inv = 1.0f / det;
+    const float inv = 1.0f / det;                                     // IEEE division: part of the exact result
     const V3 s = vsub(o, v0);
     const float uu = fdot(s, p) * inv;
     if (!(uu >= 0.0f && uu <= 1.0f)) return false;
@@ -216,12 +251,35 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
     return true;
 }
 
-constexpr int kStackDepth = 96;
+// Traversal stack: the first kSmemStack levels live in shared memory laid out [level][thread]
+// (bank = thread, conflict-free, 32-bit addressing); deeper levels spill to a per-thread local
+// array.  An LBVH over 63-bit codes plus index tie-breaks is at most 63+28 levels deep.
+constexpr int kSmemStack = 32;
+constexpr int kLocalStack = 64;
 constexpr int kSentinel = (int)0x80000000;
+
+struct Stack {
+    int* smem;          // &sStack[0][tid], stride = block size
+    int stride;
+    int sp;
+    int local[kLocalStack];
+    __device__ __forceinline__ void push(int v)
+    {
+        if (sp < kSmemStack) smem[sp * stride] = v;
+        else local[sp - kSmemStack] = v;
+        sp++;
+    }
+    __device__ __forceinline__ int pop()
+    {
+        if (sp == 0) return kSentinel;
+        sp--;
+        return (sp < kSmemStack) ? smem[sp * stride] : local[sp - kSmemStack];
+    }
+};
 
 template <bool COUNT>
 __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray& ray,
-                                            const float tmax, int* nodeCount, int* triCount)
+                                            const float tmax, int* sStackLane, int stackStride, int* nodeCount, int* triCount)
 {
     RayBox rb;
     setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, rb.sx);
@@ -229,44 +287,32 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, co
     setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, rb.sz);
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
-    int stack[kStackDepth];
-    int sp = 0;
+    Stack st;
+    st.smem = sStackLane; st.stride = stackStride; st.sp = 0;
     int cur = 0;
     int nc = 0, tc = 0;
     for (;;) {
         while (cur >= 0) {
-            const float4 n0 = __ldg(nodes + 4 * (size_t)cur);
-            const float4 n1 = __ldg(nodes + 4 * (size_t)cur + 1);
-            const float4 n2 = __ldg(nodes + 4 * (size_t)cur + 2);
-            const float4 n3 = __ldg(nodes + 4 * (size_t)cur + 3);
+            const float4* np = nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
             if (COUNT) nc++;
-            // child 0
-            float tn0 = fmaf(rb.sx ? n0.y : n0.x, rb.nix, rb.nax);
-            tn0 = fmaxf(tn0, fmaf(rb.sy ? n0.w : n0.z, rb.niy, rb.nay));
-            tn0 = fmaxf(tn0, fmaf(rb.sz ? n2.y : n2.x, rb.niz, rb.naz));
-            tn0 = fmaxf(tn0, ray.tmin);
-            float tf0 = fmaf(rb.sx ? n0.x : n0.y, rb.fix, rb.fax);
-            tf0 = fminf(tf0, fmaf(rb.sy ? n0.z : n0.w, rb.fiy, rb.fay));
-            tf0 = fminf(tf0, fmaf(rb.sz ? n2.x : n2.y, rb.fiz, rb.faz));
-            tf0 = fminf(tf0, best.t);
-            // child 1
-            float tn1 = fmaf(rb.sx ? n1.y : n1.x, rb.nix, rb.nax);
-            tn1 = fmaxf(tn1, fmaf(rb.sy ? n1.w : n1.z, rb.niy, rb.nay));
-            tn1 = fmaxf(tn1, fmaf(rb.sz ? n2.w : n2.z, rb.niz, rb.naz));
-            tn1 = fmaxf(tn1, ray.tmin);
-            float tf1 = fmaf(rb.sx ? n1.x : n1.y, rb.fix, rb.fax);
-            tf1 = fminf(tf1, fmaf(rb.sy ? n1.z : n1.w, rb.fiy, rb.fay));
-            tf1 = fminf(tf1, fmaf(rb.sz ? n2.z : n2.w, rb.fiz, rb.faz));
-            tf1 = fminf(tf1, best.t);
+            const float tn0 = fmax3(fmaf(rb.sx ? n0.y : n0.x, rb.nix, rb.nax), fmaf(rb.sy ? n0.w : n0.z, rb.niy, rb.nay),
+                                    fmaxf(fmaf(rb.sz ? n2.y : n2.x, rb.niz, rb.naz), ray.tmin));
+            const float tf0 = fmin3(fmaf(rb.sx ? n0.x : n0.y, rb.fix, rb.fax), fmaf(rb.sy ? n0.z : n0.w, rb.fiy, rb.fay),
+                                    fminf(fmaf(rb.sz ? n2.x : n2.y, rb.fiz, rb.faz), best.t));
+            const float tn1 = fmax3(fmaf(rb.sx ? n1.y : n1.x, rb.nix, rb.nax), fmaf(rb.sy ? n1.w : n1.z, rb.niy, rb.nay),
+                                    fmaxf(fmaf(rb.sz ? n2.w : n2.z, rb.niz, rb.naz), ray.tmin));
+            const float tf1 = fmin3(fmaf(rb.sx ? n1.x : n1.y, rb.fix, rb.fax), fmaf(rb.sy ? n1.z : n1.w, rb.fiy, rb.fay),
+                                    fminf(fmaf(rb.sz ? n2.z : n2.w, rb.fiz, rb.faz), best.t));
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
             const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool firstIs0 = tn0 <= tn1;          // near child first; ties -> child 0
                 cur = firstIs0 ? r0 : r1;
-                stack[sp++] = firstIs0 ? r1 : r0;
+                st.push(firstIs0 ? r1 : r0);
             } else if (h0) cur = r0;
             else if (h1) cur = r1;
-            else cur = sp ? stack[--sp] : kSentinel;
+            else cur = st.pop();
         }
         if (cur == kSentinel) break;
         const int x = ~cur;
@@ -279,7 +325,7 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, co
                 if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
             }
         }
-        cur = sp ? stack[--sp] : kSentinel;
+        cur = st.pop();
         if (cur == kSentinel) break;
     }
     if (COUNT) { *nodeCount = nc; *triCount = tc; }
@@ -341,61 +387,58 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 }
 
 // ------------------------------------------------------------------------------------------
-// K1.  One CTA owns a tile of `tileOmm` whole ommatidia (all their samples, in chunks of at most
-// kTileRays).  Lanes of a warp hold consecutive samples of one ommatidium -> coherent rays, one
-// coalesced 1 KB RNG-state read per warp.  Per-sample colour/S goes to shared memory and is then
-// summed IN SAMPLE ORDER by one thread per (ommatidium, channel): exactly the reference's
-// sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347) without its S*N*12-byte
-// global buffer round trip.
+// K1.  Persistent warps; work unit = 32 consecutive sample rays r = o*S + s (lanes hold
+// consecutive samples of one ommatidium -> coherent rays, one coalesced 1 KB RNG-state read and
+// one coalesced 384 B colour write per warp).  No block-level synchronisation: per-sample
+// colour/S (shaders.cu:730) goes to the [o][s] sample buffer and K1b sums it IN SAMPLE ORDER,
+// which is exactly the reference's sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347).
 // ------------------------------------------------------------------------------------------
 template <bool DUMP>
 __global__ void __launch_bounds__(kTraceThreads) k_traceCompound(const DeviceScene sc, const EyeParams ep)
 {
-    __shared__ float sR[kTileRays], sG[kTileRays], sB[kTileRays];
+    __shared__ int sStack[kSmemStack][kTraceThreads];
+    const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
     const float invS = 1.0f / (float)(uint32_t)ep.S;
-    for (int tile = blockIdx.x; tile < ep.nTiles; tile += gridDim.x) {
-        const int o0 = tile * ep.tileOmm;
-        const int nO = min(ep.tileOmm, ep.N - o0);
-        float carry = 0.0f;
-        for (int c0 = 0; c0 < ep.S; c0 += ep.chunk) {
-            const int nS = min(ep.chunk, ep.S - c0);
-            const int nRays = nO * nS;
-            for (int r = threadIdx.x; r < nRays; r += kTraceThreads) {
-                const int ol = r / nS;
-                const int s = c0 + (r - ol * nS);
-                const int o = o0 + ol;
-                const float4 q0 = __ldg(ep.omm + 2 * o), q1 = __ldg(ep.omm + 2 * o + 1);
-                uint4* statePtr = ep.rng + 2 * ((size_t)o * ep.S + s);
-                Rng rng = rngLoad(statePtr);
-                const Ray ray = ommatidialRay(q0, q1, ep.pose, rng);
-                rngStore(statePtr, rng);
-                const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, nullptr, nullptr);
-                const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
-                const float cr_ = col.x * invS, cg_ = col.y * invS, cb_ = col.z * invS;   // shaders.cu:730
-                sR[r] = cr_; sG[r] = cg_; sB[r] = cb_;
-                if (ep.samples) {
-                    float* dst = ep.samples + 3 * ((size_t)ep.N * s + o);
-                    dst[0] = cr_; dst[1] = cg_; dst[2] = cb_;
-                }
-                if (DUMP) {
-                    const size_t id = (size_t)ep.N * s + o;
-                    ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
-                    ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
-                    ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
-                }
-            }
-            __syncthreads();
-            for (int k = threadIdx.x; k < 3 * nO; k += kTraceThreads) {
-                const int ol = k / 3, ch = k - 3 * ol;
-                const float* src = (ch == 0 ? sR : (ch == 1 ? sG : sB)) + ol * nS;
-                float sum = (c0 == 0) ? 0.0f : carry;       // carry is only live when nO == 1 (S > chunk)
-                for (int s = 0; s < nS; s++) sum += src[s];
-                carry = sum;
-                if (c0 + nS >= ep.S) reinterpret_cast<float*>(ep.summed + o0 + ol)[ch] = sum;
-            }
-            __syncthreads();
+    const unsigned stride = gridDim.x * kTraceThreads;
+    for (unsigned r = blockIdx.x * kTraceThreads + threadIdx.x; r < total; r += stride) {
+        const unsigned o = r / (unsigned)ep.S;
+        const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
+        uint4* statePtr = ep.rng + 2 * (size_t)r;
+        Rng rng = rngLoad(statePtr);
+        const Ray ray = ommatidialRay(p0, p1, p2, ep.pose, rng);
+        rngStore(statePtr, rng);
+        const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads, nullptr, nullptr);
+        const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
+        float* dst = ep.samples + 3 * (size_t)r;
+        dst[0] = col.x * invS; dst[1] = col.y * invS; dst[2] = col.z * invS;          // shaders.cu:730
+        if (DUMP) {
+            const unsigned s = r - o * (unsigned)ep.S;
+            const size_t id = (size_t)ep.N * s + o;                                     // reference stream-id order
+            ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
+            ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
+            ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
         }
     }
+}
+
+// K1b: summed[o].ch = ((0 + c[o][0]) + c[o][1]) + ... + c[o][S-1], one thread per (ommatidium, channel).
+__global__ void k_sumSamples(const float* __restrict__ samples, int N, int S, float4* __restrict__ summed)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * N) return;
+    const int o = k / 3, ch = k - 3 * o;
+    const float* src = samples + 3 * (size_t)o * S + ch;
+    float sum = 0.0f;
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __ldg(src + 3 * (size_t)(s + j));
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += v[j];
+    }
+    for (; s < S; s++) sum += __ldg(src + 3 * (size_t)s);
+    reinterpret_cast<float*>(summed + o)[ch] = sum;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -422,7 +465,7 @@ __global__ void k_projectRaw(const float* __restrict__ samples, int N, int S, uc
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= W || y >= H || y >= S || x >= N) return;
-    const float* p = samples + 3 * ((size_t)N * y + x);
+    const float* p = samples + 3 * ((size_t)x * S + y);             // sample buffer is laid out [o][s]
     frame[(size_t)y * W + x] = makeColor(p[0], p[1], p[2]);
 }
 
@@ -517,6 +560,7 @@ __global__ void k_projectMap(bool ids, const uint32_t* __restrict__ map, const f
 __global__ void __launch_bounds__(128)
 k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1, float s2, uchar4* __restrict__ frame, int W, int H)
 {
+    __shared__ int sStack[kSmemStack][128];
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)W * H) return;
     const int x = (int)(p % W), y = (int)(p / W);
@@ -540,7 +584,7 @@ k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1,
         ray.o = vadd(vadd(C, vmuls(vmuls(X, dx), s0)), vmuls(vmuls(Y, dy), s1));
     }
     ray.tmin = 0.01f;
-    const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, nullptr, nullptr);
+    const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, nullptr, nullptr);
     const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
     frame[p] = makeColor(col.x, col.y, col.z);
 }
@@ -551,6 +595,7 @@ k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1,
 __global__ void k_traceRays(const DeviceScene sc, const float* __restrict__ origins, const float* __restrict__ dirs,
                             const float* __restrict__ tmins, int n, int4* __restrict__ hits)
 {
+    __shared__ int sStack[kSmemStack][128];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray ray;
@@ -558,7 +603,7 @@ __global__ void k_traceRays(const DeviceScene sc, const float* __restrict__ orig
     ray.d = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
     ray.tmin = tmins[i];
     int nc = 0, tc = 0;
-    const Hit h = traceClosest<true>(sc.nodes, sc.tris, ray, kTMax, &nc, &tc);
+    const Hit h = traceClosest<true>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, &nc, &tc);
     hits[2 * i] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
     hits[2 * i + 1] = make_int4(nc, tc, 0, 0);
 }
@@ -596,12 +641,21 @@ void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cuda
     k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame);
 }
 
+void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream)
+{
+    if (N <= 0) return;
+    k_prepOmmatidia<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(omm, N, pre);
+}
+
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream)
 {
-    if (eye.nTiles <= 0) return;
-    const int grid = gridBlocks < eye.nTiles ? gridBlocks : eye.nTiles;
+    const long long total = (long long)eye.N * eye.S;
+    if (total <= 0) return;
+    const long long need = (total + kTraceThreads - 1) / kTraceThreads;
+    const int grid = (int)(need < gridBlocks ? need : gridBlocks);
     if (eye.dumpHits) k_traceCompound<true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    k_sumSamples<<<(unsigned)((3 * eye.N + 127) / 128), 128, 0, stream>>>(eye.samples, eye.N, eye.S, eye.summed);
 }
 
 int traceKernelOccupancy()

@@ -106,7 +106,7 @@ DevicePose Renderer::toDevicePose(const Pose& p)
 // ------------------------------------------------------------------------------------------
 void Renderer::freeCompound(CompoundState& cs)
 {
-    dfree(cs.dOmm); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
+    dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
     cs.dumpCap = 0;
     cs.rngN = cs.rngS = 0;
@@ -324,15 +324,20 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
 {
     const int N = static_cast<int>(cam.ommatidia.size());
     cs.N = N;
+    if (static_cast<long long>(N) * cs.S >= (1ll << 31)) throw std::runtime_error("N*S must stay below 2^31 rays per frame");
     if (cs.ommDirty || !cs.dOmm) {
-        dfree(cs.dOmm);
+        dfree(cs.dOmm); dfree(cs.dPre);
         cs.dOmm = dallocT<float4>(2 * static_cast<size_t>(N));
+        cs.dPre = dallocT<float4>(3 * static_cast<size_t>(N));
         CR_CUDA(cudaMemcpyAsync(cs.dOmm, cam.ommatidia.data(), sizeof(Ommatidium) * static_cast<size_t>(N), cudaMemcpyHostToDevice, stream_));
+        launchPrepOmmatidia(cs.dOmm, N, cs.dPre, stream_);
+        launches_++;
         cs.ommDirty = false;
     }
     if (cs.rngN != N || cs.rngS != cs.S || !cs.dRng) {
         dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples);
         cs.dRng = dallocT<uint4>(2 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
+        cs.dSamples = dallocT<float>(3 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
         cs.dSummed = dallocT<float4>(static_cast<size_t>(N));
         CR_CUDA(cudaMemsetAsync(cs.dSummed, 0, sizeof(float4) * static_cast<size_t>(N ? N : 1), stream_));
         cs.rngN = N;
@@ -350,17 +355,13 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
 void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose)
 {
     EyeParams ep;
-    ep.omm = cs.dOmm;
+    ep.pre = cs.dPre;
     ep.rng = cs.dRng;
     ep.summed = cs.dSummed;
+    ep.samples = cs.dSamples;
     ep.N = cs.N;
     ep.S = cs.S;
     ep.pose = toDevicePose(pose);
-    const int mode = projectionFromName(cam.projection);
-    if (mode == PROJ_RAW_SAMPLES) {
-        if (!cs.dSamples) cs.dSamples = dallocT<float>(3 * static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S));
-        ep.samples = cs.dSamples;
-    }
     if (dumpRays) {
         const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
         if (cs.dumpCap < need) {
@@ -372,19 +373,9 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
         }
         ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH;
     }
-    // tiling: whole ommatidia per CTA tile, enough tiles to fill the machine when the frame allows
-    const long long totalRays = static_cast<long long>(cs.N) * cs.S;
-    const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
-    long long target = totalRays / (slots > 0 ? slots : 1);
-    target = std::max<long long>(kTraceThreads, std::min<long long>(kTileRays, target));
-    if (cs.S >= kTileRays) { ep.chunk = kTileRays; ep.tileOmm = 1; }
-    else {
-        ep.chunk = cs.S;
-        ep.tileOmm = static_cast<int>(std::max<long long>(1, std::min<long long>(kTileRays / cs.S, target / cs.S)));
-    }
-    ep.nTiles = (cs.N + ep.tileOmm - 1) / ep.tileOmm;
+    const long long slots = static_cast<long long>(numSMs_) * traceOcc_;   // persistent grid: every SM full
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
-    launches_++;
+    launches_ += 2;   // trace + ordered sum
     cs.frameIndex++;
 }
 

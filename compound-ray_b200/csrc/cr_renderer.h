@@ -19,9 +19,10 @@ namespace cr {
 
 struct CompoundState {                 // device side of one CompoundEye camera
     float4* dOmm = nullptr;
+    float4* dPre = nullptr;            // per-ommatidium ray invariants
     uint4* dRng = nullptr;
     float4* dSummed = nullptr;
-    float* dSamples = nullptr;         // only for raw_ommatidial_samples
+    float* dSamples = nullptr;         // per-sample colour/S, [o][s]
     uint32_t* dMap = nullptr;          // cached pixel -> ommatidium map
     int mapMode = -2, mapW = 0, mapH = 0;
     uint64_t mapEyeVersion = 0, eyeVersion = 1;
