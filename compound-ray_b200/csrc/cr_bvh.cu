@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -351,6 +352,12 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
         extMax = fmaxf(extMax, ext);
     }
     bc.padAbs = extMax * 1.1920929e-07f;
+    // Morton quantisation grid: one uniform cube of the largest extent (default) keeps cells
+    // cubical, so flat scenes (terrain) are not split along their thin axis at the top levels;
+    // CR_MORTON_PER_AXIS=1 restores per-axis normalisation.
+    const char* perAxis = getenv("CR_MORTON_PER_AXIS");
+    if (!(perAxis && atoi(perAxis) != 0))
+        for (int a = 0; a < 3; a++) bc.invExt[a] = extMax > 0.0f ? 1.0f / extMax : 0.0f;
 
     float4* leafMin = dalloc<float4>(n);
     float4* leafMax = dalloc<float4>(n);

@@ -254,7 +254,13 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
 // Traversal stack: the first kSmemStack levels live in shared memory laid out [level][thread]
 // (bank = thread, conflict-free, 32-bit addressing); deeper levels spill to a per-thread local
 // array.  An LBVH over 63-bit codes plus index tie-breaks is at most 63+28 levels deep.
-constexpr int kSmemStack = 32;
+#ifndef CR_TRACE_MIN_BLOCKS
+#define CR_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef CR_SMEM_STACK
+#define CR_SMEM_STACK 32
+#endif
+constexpr int kSmemStack = CR_SMEM_STACK;
 constexpr int kLocalStack = 64;
 constexpr int kSentinel = (int)0x80000000;
 
@@ -394,7 +400,7 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 // which is exactly the reference's sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347).
 // ------------------------------------------------------------------------------------------
 template <bool DUMP>
-__global__ void __launch_bounds__(kTraceThreads) k_traceCompound(const DeviceScene sc, const EyeParams ep)
+__global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCompound(const DeviceScene sc, const EyeParams ep)
 {
     __shared__ int sStack[kSmemStack][kTraceThreads];
     const unsigned total = (unsigned)ep.N * (unsigned)ep.S;

@@ -53,7 +53,7 @@ class Ommatidium:
 
 def load_library(path: str | None = None, device: int | None = None):
     """dlopen the renderer, declare the signatures and optionally pin the CUDA device."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("CR_LIB_PATH") or LIB_PATH
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not found: build it with `make -C {_HERE}` (nvcc, sm_100a)")
     lib = C.CDLL(path)
