@@ -263,6 +263,20 @@ void crDebugCopyOmmatidia(float* out8)
     if (!o.empty()) memcpy(out8, o.data(), sizeof(cr::Ommatidium) * o.size());
 }
 int crDebugGetMissShader(void) { return renderer().scene().missShader; }
+size_t crDebugGetTextureCount(void) { return renderer().scene().textures.size(); }
+void crDebugGetTextureSize(int index, int* w, int* h)
+{
+    const auto& t = renderer().scene().textures;
+    if (index < 0 || static_cast<size_t>(index) >= t.size()) { *w = 0; *h = 0; return; }
+    *w = t[static_cast<size_t>(index)].width;
+    *h = t[static_cast<size_t>(index)].height;
+}
+void crDebugCopyTexture(int index, unsigned char* outRgba)
+{
+    const auto& t = renderer().scene().textures;
+    if (index < 0 || static_cast<size_t>(index) >= t.size()) return;
+    memcpy(outRgba, t[static_cast<size_t>(index)].pixels.data(), t[static_cast<size_t>(index)].pixels.size());
+}
 size_t crDebugGetBvhNodeCount(void) { return static_cast<size_t>(renderer().debugNodeCount()); }
 void crDebugCopyBvh(float* nodes16, float* tris12)
 {

@@ -153,6 +153,7 @@ void Renderer::loadScene(const std::string& path)
     scene_ = std::move(sc);
     loaded_ = true;
     current_ = 0;
+    (void)camera();   // finalize() touches getCamera(), which creates the default camera (MulticamScene.cpp:855-857,911-927)
     int count = 0;
     if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0) {
         ensureDevice();

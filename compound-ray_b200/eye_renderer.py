@@ -109,7 +109,10 @@ def configureFunctions(eyeRenderer):
     r.crGetLastTraceMs.restype = C.c_double
     r.crGetLaunchCount.restype = C.c_ulonglong
     r.crGetBvhBuildMs.restype = C.c_double
-    for name in ("crDebugGetTriangleCount", "crDebugGetVertexCount", "crDebugGetMeshCount", "crDebugGetBvhNodeCount"):
+    r.crDebugGetTextureSize.argtypes = [C.c_int, vp, vp]
+    r.crDebugCopyTexture.argtypes = [C.c_int, vp]
+    for name in ("crDebugGetTriangleCount", "crDebugGetVertexCount", "crDebugGetMeshCount", "crDebugGetBvhNodeCount",
+                 "crDebugGetTextureCount"):
         getattr(r, name).restype = C.c_size_t
     r.crDebugCopyTriangles.argtypes = [vp]
     r.crDebugCopyTriangleMesh.argtypes = [vp]

@@ -1,0 +1,45 @@
+"""Pose sharding across GPUs -- host-side logic only, no device code.
+
+The path shards by camera pose: rank r of R renders the contiguous pose block
+[lo, hi) of a P-pose run; scene, BVH and eye are replicated per GPU; the only exchange is the
+final allgather of the per-pose uchar4 rows.  Results must not depend on the sharding: the
+reference semantics are "pose k is frame k of every sample stream", so a rank whose block starts at
+pose lo positions its RNG streams at frame lo (crSetFirstFrame) before rendering.
+"""
+from __future__ import annotations
+
+
+def pose_block(rank: int, world: int, n_poses: int) -> tuple[int, int]:
+    """Contiguous block of poses for `rank`; blocks differ by at most one pose."""
+    base, extra = divmod(n_poses, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def padded_block_size(world: int, n_poses: int) -> int:
+    """Rows per rank in the allgather buffer (equal counts; short blocks are padded)."""
+    return -(-n_poses // world)
+
+
+def draws_before_frame(k: int) -> int:
+    """Raw XORWOW draws one stream has consumed before frame k (3 on even frames, 1 on odd)."""
+    return 3 * ((k + 1) // 2) + (k // 2)
+
+
+def gathered_row(rank: int, local_index: int, world: int, n_poses: int) -> int:
+    """Row of pose (rank, local_index) in the padded allgather result."""
+    return rank * padded_block_size(world, n_poses) + local_index
+
+
+def unpad(gathered, world: int, n_poses: int):
+    """Drop the padding rows of an allgathered [world*block, ...] array -> [n_poses, ...]."""
+    blk = padded_block_size(world, n_poses)
+    parts = []
+    for r in range(world):
+        lo, hi = pose_block(r, world, n_poses)
+        parts.append(gathered[r * blk: r * blk + (hi - lo)])
+    import numpy as np
+    if isinstance(gathered, np.ndarray):
+        return np.concatenate(parts, axis=0)
+    import torch
+    return torch.cat(parts, dim=0)

@@ -124,6 +124,9 @@ void crDebugCopyCameraScale(float* out3);
 int crDebugGetCameraKind(void);                  /* 0 perspective, 1 panoramic, 2 orthographic, 3 compound */
 void crDebugCopyOmmatidia(float* out8);
 int crDebugGetMissShader(void);
+size_t crDebugGetTextureCount(void);
+void crDebugGetTextureSize(int index, int* w, int* h);
+void crDebugCopyTexture(int index, unsigned char* outRgba);   /* decoded RGBA8, row 0 first */
 size_t crDebugGetBvhNodeCount(void);
 void crDebugCopyBvh(float* nodes16, float* tris12);
 void crDebugSetRayDump(bool on);

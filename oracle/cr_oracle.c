@@ -178,6 +178,23 @@ API float cro_xorwow_normal(xw_state* s)
 API unsigned long long cro_draws_before_frame(unsigned long long k)
 { return 3ull * ((k + 1) / 2) + (k / 2); }
 
+/* Streams positioned as if `first_frame` frames had already been rendered: frame
+ * pairs consume 3 + 1 draws; an odd frame count additionally replays one frame's draws so the
+ * Box-Muller cache and flag are populated exactly as in the sequential run. */
+API void cro_position_streams(xw_state* states, int64_t N, int64_t S, unsigned long long first_frame)
+{
+    cro_xorwow_build_tables();
+    #pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < N * S; id++) {
+        xw_state st;
+        cro_xorwow_init(&st, 42ull, (unsigned long long)id, 0ull);
+        const unsigned long long even = first_frame & ~1ull;
+        if (even) cro_xorwow_skipahead(&st, 2ull * even);
+        if (first_frame & 1ull) { (void)cro_xorwow_normal(&st); (void)cro_xorwow_uniform(&st); }
+        states[id] = st;
+    }
+}
+
 /* =====================================================================================
  *  2. Ommatidial sample rays   (libEyeRenderer3/shaders.cu:648-662, 664-709)
  * ===================================================================================== */

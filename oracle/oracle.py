@@ -80,6 +80,7 @@ def lib():
         L.cro_xorwow_uniform.restype = f32
         L.cro_draws_before_frame.argtypes = [C.c_ulonglong]
         L.cro_draws_before_frame.restype = C.c_ulonglong
+        L.cro_position_streams.argtypes = [vp, i64, i64, C.c_ulonglong]
         L.cro_generate_rays.argtypes = [vp, i64, i64, C.POINTER(Pose), vp, C.c_int, vp, vp, vp]
         L.cro_trace_bruteforce.argtypes = [vp, i64, vp, vp, vp, i64, f32, vp]
         L.cro_bvh_build.argtypes = [vp, i64]
@@ -277,6 +278,12 @@ class CompoundEyeOracle:
             self.states = np.zeros(len(omm) * self.S, dtype=STATE_DTYPE)
             self.configured = False
         self.omm = omm
+
+    def set_first_frame(self, k):
+        """Position every stream as if k frames had been rendered (pose sharding / restart)."""
+        self.states = np.zeros(len(self.omm) * self.S, dtype=STATE_DTYPE)
+        lib().cro_position_streams(_p(self.states), len(self.omm), self.S, int(k))
+        self.configured = True
 
     def set_render_size(self, w, h):
         self.W, self.H = int(w), int(h)

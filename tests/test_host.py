@@ -1,0 +1,273 @@
+"""CPU tests of the product's host side through the C ABI (no GPU needed, no compute calls):
+exports, loader parity with the oracle's independent numpy loader, pose arithmetic, camera
+navigation semantics, hit-geometry queries, error behaviour without a device."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "libEyeRenderer.h")).read()
+    body = hdr[hdr.index('extern "C" {'):]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"^\s*(?:[\w\*]+\s+)+\*?(\w+)\s*\(", body, flags=re.M)
+    return [n for n in names if n not in ("defined",)]
+
+
+REFERENCE_ABI = """setVerbosity loadGlTFscene stop setRenderSize renderFrame displayFrame saveFrameAs getFramePointer
+getCameraCount nextCamera previousCamera getCurrentCameraIndex getCurrentCameraName gotoCamera gotoCameraByName
+setCameraPosition getCameraPosition setCameraLocalSpace rotateCameraAround rotateCameraLocallyAround translateCamera
+translateCameraLocally resetCameraPose setCameraPose isCompoundEyeActive setCurrentEyeSamplesPerOmmatidium
+getCurrentEyeSamplesPerOmmatidium changeCurrentEyeSamplesPerOmmatidiumBy getCurrentEyeOmmatidialCount setOmmatidia
+getCurrentEyeDataPath setCurrentEyeShaderName isInsideHitGeometry getGeometryMaxBounds getGeometryMinBounds""".split()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(REFERENCE_ABI) == 35
+    for name in REFERENCE_ABI:
+        assert name in declared, f"{name} missing from include/libEyeRenderer.h"
+    assert len(declared) >= 35 + 20
+    for name in declared:
+        assert hasattr(lib, name), f"libEyeRenderer3.so does not export {name}"
+    out = subprocess.run(["nm", "-D", "--defined-only", lib._name], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(REFERENCE_ABI) <= exported
+
+
+def test_library_has_no_gl_or_optix_dependency(lib):
+    out = subprocess.run(["ldd", lib._name], capture_output=True, text=True).stdout.lower()
+    for bad in ("optix", "libgl", "glfw", "x11"):
+        assert bad not in out
+
+
+def _copy(lib, fn, shape, dtype=np.float32):
+    a = np.zeros(shape, dtype)
+    getattr(lib, fn)(a.ctypes.data)
+    return a
+
+
+@pytest.mark.parametrize("rel", ["data/test-scene/test-scene.gltf", "data/test-scene/test-scene-sky.gltf",
+                                 "data/natural-standin-sky.gltf", "sim-environment/env_2.gltf"])
+def test_loader_parity_with_oracle_loader(lib, loader, ref_data, rel):
+    path = os.path.join(ref_data, rel)
+    lib.loadGlTFscene(path.encode())
+    sc = loader.load_scene(path)
+    T = lib.crDebugGetTriangleCount()
+    assert T == len(sc.tris)
+    tris = _copy(lib, "crDebugCopyTriangles", (T, 9))
+    assert np.array_equal(tris.view(np.uint32), sc.tris.view(np.uint32)), "world-space triangles (v0,e1,e2) bit-exact"
+    assert np.array_equal(_copy(lib, "crDebugCopyTriangleMesh", T, np.int32), sc.tri_mesh)
+    uv = np.zeros((T, 3, 2), np.float32); col = np.zeros((T, 3, 4), np.float32)
+    lib.crDebugCopyCornerAttributes(uv.ctypes.data, col.ctypes.data)
+    assert np.array_equal(uv, sc.corner_uv) and np.array_equal(col, sc.corner_col)
+    M = lib.crDebugGetMeshCount()
+    assert M == len(sc.mesh_info)
+    info = np.zeros((M, 4), np.int32); base = np.zeros((M, 4), np.float32)
+    lib.crDebugCopyMeshInfo(info.ctypes.data, base.ctypes.data)
+    for i, mi in enumerate(sc.mesh_info):
+        assert (info[i, 0], info[i, 1], info[i, 2]) == (mi["color_type"], mi["has_uv"], mi["tex"])
+        assert np.array_equal(base[i], mi["base_color"])
+    assert lib.crDebugGetMissShader() == {"default_background": 0, "simple_sky": 1}[sc.miss_shader]
+    # cameras: same order, names, kinds, poses (bit-exact), eyes
+    kinds = {"perspective": 0, "panoramic": 1, "orthographic": 2, "compound": 3}
+    assert lib.getCameraCount() == len(sc.cameras)
+    for i, cam in enumerate(sc.cameras):
+        lib.gotoCamera(i)
+        assert lib.getCurrentCameraName().decode() == cam.name
+        assert lib.crDebugGetCameraKind() == kinds[cam.kind]
+        pose = _copy(lib, "crDebugCopyCameraPose", 12)
+        want = np.concatenate([cam.position, cam.x_axis, cam.y_axis, cam.z_axis]).astype(np.float32)
+        assert np.array_equal(pose.view(np.uint32), want.view(np.uint32))
+        if cam.kind == "compound":
+            assert lib.isCompoundEyeActive() and lib.getCurrentEyeOmmatidialCount() == len(cam.ommatidia)
+            omm = _copy(lib, "crDebugCopyOmmatidia", (len(cam.ommatidia), 8))
+            assert np.array_equal(omm.view(np.uint32), cam.ommatidia.view(np.uint32))
+            assert lib.getCurrentEyeDataPath().decode() == cam.eye_path
+            assert lib.getCurrentEyeSamplesPerOmmatidium() == 1
+        else:
+            assert not lib.isCompoundEyeActive()
+            assert lib.getCurrentEyeSamplesPerOmmatidium() == -1 and lib.getCurrentEyeOmmatidialCount() == 0
+            assert lib.getCurrentEyeDataPath() == b""
+            if cam.kind != "perspective":
+                assert np.array_equal(_copy(lib, "crDebugCopyCameraScale", 3)[:2], cam.scale[:2])
+            else:
+                assert np.allclose(_copy(lib, "crDebugCopyCameraScale", 3), cam.scale, rtol=1e-6)
+    # textures: own PNG decoder vs PIL
+    assert lib.crDebugGetTextureCount() == len(sc.textures)
+    for i, t in enumerate(sc.textures):
+        w, h = C.c_int(), C.c_int()
+        lib.crDebugGetTextureSize(i, C.byref(w), C.byref(h))
+        assert (h.value, w.value) == t.shape[:2]
+        px = np.zeros(t.shape, np.uint8)
+        lib.crDebugCopyTexture(i, px.ctypes.data)
+        assert np.array_equal(px, t)
+    # world AABB queries for render meshes
+    for m in sc.meshes:
+        lo = lib.getGeometryMinBounds(m.name.encode()); hi = lib.getGeometryMaxBounds(m.name.encode())
+        assert np.array_equal(np.float32([lo.x, lo.y, lo.z]), m.world_min) and np.array_equal(np.float32([hi.x, hi.y, hi.z]), m.world_max)
+    z = lib.getGeometryMaxBounds(b"no-such-geometry")
+    assert (z.x, z.y, z.z) == (0.0, 0.0, 0.0)
+
+
+def test_camera_navigation_semantics(lib, ref_data):
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    n = lib.getCameraCount()
+    assert n == 6 and lib.getCurrentCameraIndex() == 0
+    lib.previousCamera()
+    assert lib.getCurrentCameraIndex() == 5                               # wraps
+    lib.nextCamera()
+    assert lib.getCurrentCameraIndex() == 0
+    lib.gotoCamera(-1)
+    assert lib.getCurrentCameraIndex() == 5
+    lib.gotoCamera(14)
+    assert lib.getCurrentCameraIndex() == 2
+    assert lib.gotoCameraByName(b"insect-cam-2") and lib.getCurrentCameraIndex() == 5
+    assert not lib.gotoCameraByName(b"nope") and lib.getCurrentCameraIndex() == 0   # miss: false, camera 0
+    # per-camera state: S and ommatidia belong to the camera
+    lib.gotoCameraByName(b"insect-cam-1")
+    lib.setCurrentEyeSamplesPerOmmatidium(17)
+    lib.changeCurrentEyeSamplesPerOmmatidiumBy(-30)
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == 1                   # max(1, s)
+    lib.changeCurrentEyeSamplesPerOmmatidiumBy(4)
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == 5
+    lib.gotoCameraByName(b"insect-cam-2")
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == 1
+    lib.gotoCameraByName(b"Camera")
+    lib.setCurrentEyeSamplesPerOmmatidium(9)                              # ignored on non-compound cameras
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == -1
+
+
+def test_pose_api_matches_oracle_pose_math(lib, er, oracle, ref_data):
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    lib.gotoCamera(2)
+    lib.setCameraPose(1.5, -2.0, 0.25, 0.3, -1.1, 2.5)
+    want = oracle.set_camera_pose(1.5, -2.0, 0.25, 0.3, -1.1, 2.5)
+    got = _copy(lib, "crDebugCopyCameraPose", 12)
+    ref = np.float32(list(want.pos) + list(want.ax) + list(want.ay) + list(want.az))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    x, y, z = C.c_float(), C.c_float(), C.c_float()
+    lib.getCameraPosition(C.byref(x), C.byref(y), C.byref(z))
+    assert (x.value, y.value, z.value) == (1.5, -2.0, 0.25)
+    # local moves / rotations follow cameras/DataRecordCamera.h:57-82
+    lib.resetCameraPose()
+    lib.rotateCameraAround(np.float32(np.pi / 2), 0, 2, 0)                # axis is normalised
+    lib.translateCameraLocally(0, 0, 1)                                   # +z local = world +x after the turn
+    p = _copy(lib, "crDebugCopyCameraPose", 12)
+    assert np.allclose(p[0:3], [1, 0, 0], atol=1e-6) and np.allclose(p[9:12], [1, 0, 0], atol=1e-6)
+    lib.rotateCameraLocallyAround(np.float32(np.pi / 2), 0, 0, 1)         # roll about the local z axis
+    p = _copy(lib, "crDebugCopyCameraPose", 12)
+    assert np.allclose(p[3:6], [0, 1, 0], atol=1e-6) and np.allclose(p[9:12], [1, 0, 0], atol=1e-6)
+    lib.translateCamera(0, 0, -3)
+    m = np.eye(3, dtype=np.float32)[:, ::-1]
+    er.setCameraLocalSpace(lib, m)
+    p = _copy(lib, "crDebugCopyCameraPose", 12)
+    assert np.allclose(p[0:3], [1, 0, -3], atol=1e-6) and np.array_equal(p[3:6], m[:, 0]) and np.array_equal(p[9:12], m[:, 2])
+
+
+def test_set_ommatidia_and_helper_roundtrip(lib, er, ref_data, tmp_path):
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    er.gotoFirstCompoundEye(lib)
+    assert lib.getCurrentCameraName() == b"insect-cam-1"
+    ico = er.getIcoOmmatidia()
+    assert len(ico) == 12 and abs(ico[0].getSolidAngle() - 1.0) < 1e-9
+    er.setOmmatidiaFromOmmatidiumList(lib, ico)
+    assert lib.getCurrentEyeOmmatidialCount() == 12
+    got = _copy(lib, "crDebugCopyOmmatidia", (12, 8))
+    assert np.allclose(got[:, 3:6], [o.direction for o in ico], atol=1e-7)
+    p = tmp_path / "ico.eye"
+    er.saveEyeFile(str(p), ico)
+    back = er.readEyeFile(str(p))
+    assert len(back) == 12 and np.allclose(back[5].direction, ico[5].direction, atol=1e-9)
+    er.gotoFirstRegularCamera(lib)
+    assert lib.getCurrentCameraName() == b"Camera"
+    assert er.decodeProjectionMapID(np.array([0x12, 0x34, 0x56, 0x78], np.uint8)) == 0x12345678
+
+
+def test_hit_geometry_queries(lib, tmp_path):
+    """isInsideHitGeometry / bounds on a hitbox mesh (MulticamScene.cpp:329-345,1757-1818), including the
+    reference quirk that the query point is transformed with w = 0 (node translation ignored)."""
+    import base64
+    v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], np.float32)
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    idx = np.array([[a, b, c, a, c, d] for a, b, c, d in quads], np.uint16).reshape(-1)
+    blob = v.tobytes() + idx.tobytes()
+    gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}],
+            "nodes": [{"mesh": 0, "name": "box", "scale": [2, 2, 2], "translation": [10, 0, 0]}],
+            "meshes": [{"name": "arena", "extras": {"hitbox": True}, "primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 8, "type": "VEC3", "min": [-1, -1, -1], "max": [1, 1, 1]},
+                          {"bufferView": 1, "componentType": 5123, "count": 36, "type": "SCALAR"}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 96}, {"buffer": 0, "byteOffset": 96, "byteLength": 72}],
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    p = tmp_path / "hb.gltf"
+    p.write_text(json.dumps(gltf))
+    lib.loadGlTFscene(str(p).encode())
+    assert lib.crDebugGetTriangleCount() == 0                            # hitbox meshes are not rendered
+    assert lib.getCameraCount() == 1 and lib.getCurrentCameraName() == b"Default Camera"
+    hi = lib.getGeometryMaxBounds(b"arena"); lo = lib.getGeometryMinBounds(b"arena")
+    assert (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) == (8.0, -2.0, -2.0, 12.0, 2.0, 2.0)
+    # scale 2 => object-space test of p/2 against the unit cube; translation ignored (w = 0)
+    assert lib.isInsideHitGeometry(0.5, 0.3, -0.7, b"arena")            # (a point on a face diagonal counts twice: reference quirk)
+    assert not lib.isInsideHitGeometry(0.5, 0.5, 0.5, b"arena")
+    assert lib.isInsideHitGeometry(1.9, -1.9, 1.0, b"arena")
+    assert not lib.isInsideHitGeometry(2.5, 0.0, 0.0, b"arena")
+    assert not lib.isInsideHitGeometry(10.0, 5.0, 0.0, b"arena")
+    assert not lib.isInsideHitGeometry(0, 0, 0, b"missing")
+
+
+def test_no_cpu_fallback_render_fails_loudly(ref_data):
+    """Without a CUDA device renderFrame reports an error and returns 0 -- it never renders on the CPU."""
+    code = f"""
+import sys
+sys.path.insert(0, {os.path.join(ROOT, 'compound-ray_b200')!r})
+import eye_renderer as er
+L = er.load_library(); L.setVerbosity(False)
+L.loadGlTFscene({os.path.join(ref_data, 'data', 'test-scene', 'test-scene.gltf')!r}.encode())
+L.gotoCamera(2)
+print('MS', L.renderFrame(), L.crGetLaunchCount())
+"""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert "MS 0.0 0" in r.stdout
+    assert "no CUDA device available" in r.stderr and "no CPU path" in r.stderr
+
+
+def test_malformed_inputs_are_reported_not_thrown(lib, tmp_path, capfd):
+    lib.loadGlTFscene(b"/nonexistent/scene.gltf")
+    p = tmp_path / "broken.gltf"
+    p.write_text("{ \"asset\": ")
+    lib.loadGlTFscene(str(p).encode())
+    err = capfd.readouterr().err
+    assert err.count("[PyEye] ERROR") == 2
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/python-examples/eyeRendererHelperFunctions.py"),
+                    reason="reference tree not present on this machine")
+def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
+    """The reference's own ctypes helper configures and drives this library unchanged."""
+    sys.path.insert(0, "/root/reference/python-examples")
+    try:
+        import eyeRendererHelperFunctions as ref_helper
+    finally:
+        sys.path.pop(0)
+    L = C.CDLL(lib._name)
+    ref_helper.configureFunctions(L)
+    L.setVerbosity(False)
+    L.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    ref_helper.gotoFirstCompoundEye(L)
+    assert L.getCurrentCameraName() == b"insect-cam-1" and L.getCurrentEyeOmmatidialCount() == 1000
+    ref_helper.setOmmatidiaFromOmmatidiumList(L, ref_helper.getIcoOmmatidia())
+    assert L.getCurrentEyeOmmatidialCount() == 12
+    ref_helper.setRenderSize(L, 12, 1)
+    ref_helper.setCameraLocalSpace(L, np.eye(3))
+    b = L.getGeometryMaxBounds(b"Cube")
+    assert b.toNumpy().tolist() == [1.0, 1.0, 1.0]
+    assert ref_helper.readEyeFile(os.path.join(ref_data, "data", "test-scene", "test100.eye"))[99].acceptanceAngle == 1.0
