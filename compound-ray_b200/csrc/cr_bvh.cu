@@ -9,7 +9,8 @@
 //      (block histograms -> exclusive scan -> stable scatter with warp match ranking)
 //   3. Karras 2012 hierarchy from the sorted codes (ties broken by position)
 //   4. bottom-up AABB refit with one atomic arrival counter per internal node
-//   5. emit: 64-byte nodes holding both child boxes, subtrees of <= leafSize triangles folded
+//   5. emit: 64-byte nodes holding both child boxes (x8 direction-octant variants, near/far
+//      pre-selected), subtrees of <= leafSize triangles folded
 //      into leaf references, and 48-byte (v0, e1, e2, prim) triangle records in tree order.
 // HBM-bound integer/byte work; every kernel is a flat grid-stride or one-thread-per-item pass.
 #include <chrono>
@@ -264,19 +265,30 @@ __device__ __forceinline__ int childRef(int c, int n, const int2* __restrict__ r
     return c;
 }
 
+// Every node is emitted 8 times, once per ray-direction sign octant v = sx | sy<<1 | sz<<2, with
+// each child box stored as (near, far) for that octant: near = max, far = min on axes whose
+// direction component is negative.  The traversal loop then needs no per-node selects.  All rays
+// of a frame leave one eye, so an octant's rays visit their own region of the tree and the cached
+// working set does not grow with the 8x footprint (HBM is plentiful: 64 B x 8 per node).
 __global__ void k_emitNodes(int n, const int2* __restrict__ children, const int2* __restrict__ ranges,
                             const float4* __restrict__ boxMin, const float4* __restrict__ boxMax, int leafSize,
-                            float4* __restrict__ nodes)
+                            float4* __restrict__ nodes, size_t variantStride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int2 c = children[i];
     const float4 a0 = boxMin[c.x], a1 = boxMax[c.x], b0 = boxMin[c.y], b1 = boxMax[c.y];
     const int r0 = childRef(c.x, n, ranges, leafSize), r1 = childRef(c.y, n, ranges, leafSize);
-    nodes[4 * (size_t)i + 0] = make_float4(a0.x, a1.x, a0.y, a1.y);
-    nodes[4 * (size_t)i + 1] = make_float4(b0.x, b1.x, b0.y, b1.y);
-    nodes[4 * (size_t)i + 2] = make_float4(a0.z, a1.z, b0.z, b1.z);
-    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.0f, 0.0f);
+    const float4 refs = make_float4(__int_as_float(r0), __int_as_float(r1), 0.0f, 0.0f);
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        const bool sx = v & 1, sy = v & 2, sz = v & 4;
+        float4* out = nodes + (size_t)v * variantStride + 4 * (size_t)i;
+        out[0] = make_float4(sx ? a1.x : a0.x, sx ? a0.x : a1.x, sy ? a1.y : a0.y, sy ? a0.y : a1.y);
+        out[1] = make_float4(sx ? b1.x : b0.x, sx ? b0.x : b1.x, sy ? b1.y : b0.y, sy ? b0.y : b1.y);
+        out[2] = make_float4(sz ? a1.z : a0.z, sz ? a0.z : a1.z, sz ? b1.z : b0.z, sz ? b0.z : b1.z);
+        out[3] = refs;
+    }
 }
 
 // n == 1 (or the whole scene fits one leaf): a root whose child 0 is the leaf and child 1 is empty
@@ -285,11 +297,16 @@ __global__ void k_emitSingleRoot(int n, const float4* __restrict__ rootMin, cons
 {
     const float4 a0 = rootMin[0], a1 = rootMax[0];
     const float inf = __int_as_float(0x7f800000);
-    nodes[0] = make_float4(a0.x, a1.x, a0.y, a1.y);
-    nodes[1] = make_float4(inf, -inf, inf, -inf);
-    nodes[2] = make_float4(a0.z, a1.z, inf, -inf);
     const int r0 = ~((0 << 3) | (n - 1));
-    nodes[3] = make_float4(__int_as_float(r0), __int_as_float(r0), 0.0f, 0.0f);
+    for (int v = 0; v < 8; v++) {
+        const bool sx = v & 1, sy = v & 2, sz = v & 4;
+        float4* out = nodes + 4 * (size_t)v;
+        // child 1 is empty: near = +inf, far = -inf in every octant
+        out[0] = make_float4(sx ? a1.x : a0.x, sx ? a0.x : a1.x, sy ? a1.y : a0.y, sy ? a0.y : a1.y);
+        out[1] = make_float4(inf, -inf, inf, -inf);
+        out[2] = make_float4(sz ? a1.z : a0.z, sz ? a0.z : a1.z, inf, -inf);
+        out[3] = make_float4(__int_as_float(r0), __int_as_float(r0), 0.0f, 0.0f);
+    }
 }
 
 __global__ void k_emitTris(const float* __restrict__ pos, const uint32_t* __restrict__ idx, int n,
@@ -329,14 +346,19 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
     if (nTris == 0) {
         // a root with two empty children: every ray misses
         out.nNodes = 1;
-        out.nodes = dalloc<float4>(4);
+        out.nodes = dalloc<float4>(4 * 8);
         out.tris = dalloc<float4>(3);
         const float inf = INFINITY;
         const int emptyRef = ~0;   // first 0, count 1 -- never visited because the boxes are empty
-        float4 h[4] = {make_float4(inf, -inf, inf, -inf), make_float4(inf, -inf, inf, -inf), make_float4(inf, -inf, inf, -inf),
-                       make_float4(0, 0, 0, 0)};
-        memcpy(&h[3].x, &emptyRef, 4);
-        memcpy(&h[3].y, &emptyRef, 4);
+        float4 h[32];
+        for (int v = 0; v < 8; v++) {
+            h[4 * v + 0] = make_float4(inf, -inf, inf, -inf);
+            h[4 * v + 1] = make_float4(inf, -inf, inf, -inf);
+            h[4 * v + 2] = make_float4(inf, -inf, inf, -inf);
+            h[4 * v + 3] = make_float4(0, 0, 0, 0);
+            memcpy(&h[4 * v + 3].x, &emptyRef, 4);
+            memcpy(&h[4 * v + 3].y, &emptyRef, 4);
+        }
         CR_CUDA(cudaMemcpyAsync(out.nodes, h, sizeof h, cudaMemcpyHostToDevice, stream));
         CR_CUDA(cudaMemsetAsync(out.tris, 0, sizeof(float4) * 3, stream));
         CR_CUDA(cudaStreamSynchronize(stream));
@@ -400,7 +422,7 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
         CR_CUDA(cudaMemcpyAsync(boxMin, &mn, sizeof mn, cudaMemcpyHostToDevice, stream));
         CR_CUDA(cudaMemcpyAsync(boxMax, &mx, sizeof mx, cudaMemcpyHostToDevice, stream));
         out.nNodes = 1;
-        out.nodes = dalloc<float4>(4);
+        out.nodes = dalloc<float4>(4 * 8);
         k_emitSingleRoot<<<1, 1, 0, stream>>>(n, boxMin, boxMax, out.nodes);
     } else {
         int* parent = dalloc<int>((size_t)2 * n);
@@ -412,8 +434,8 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
         k_buildHierarchy<<<gridI, tpb, 0, stream>>>(keysA, n, parent, children, ranges);
         k_refit<<<gridN, tpb, 0, stream>>>(n, valsA, leafMin, leafMax, parent, children, boxMin, boxMax, arrivals);
         out.nNodes = n - 1;
-        out.nodes = dalloc<float4>((size_t)4 * (n - 1));
-        k_emitNodes<<<gridI, tpb, 0, stream>>>(n, children, ranges, boxMin, boxMax, leafSize, out.nodes);
+        out.nodes = dalloc<float4>((size_t)4 * (n - 1) * 8);
+        k_emitNodes<<<gridI, tpb, 0, stream>>>(n, children, ranges, boxMin, boxMax, leafSize, out.nodes, (size_t)4 * (n - 1));
         CR_CUDA(cudaStreamSynchronize(stream));
         cudaFree(parent); cudaFree(children); cudaFree(ranges); cudaFree(arrivals);
     }

@@ -1,10 +1,12 @@
 // cr_device.h -- device-side data layout shared by the builder, the kernels and the renderer.
 //
 // HBM layout (all buffers 256-byte aligned by cudaMalloc):
-//   nodes   float4[4*nNodes]   64 B per BVH2 node, both child boxes inline:
-//             n[0] = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
-//             n[1] = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
-//             n[2] = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
+//   nodes   float4[8][4*nNodes] 64 B per BVH2 node, both child boxes inline, stored once per
+//           ray-direction sign octant v = sx | sy<<1 | sz<<2 with (near, far) planes pre-selected
+//           (variant 0 = (min, max) on every axis):
+//             n[0] = (c0.near.x, c0.far.x, c0.near.y, c0.far.y)
+//             n[1] = (c1.near.x, c1.far.x, c1.near.y, c1.far.y)
+//             n[2] = (c0.near.z, c0.far.z, c1.near.z, c1.far.z)
 //             n[3] = (ref0, ref1, unused, unused) as int bits
 //           child ref >= 0 : internal node index;  ref < 0 : leaf,  x = ~ref,
 //           first triangle = x >> 3 (position in the sorted array), count = (x & 7) + 1
@@ -43,6 +45,7 @@ struct DeviceScene {
     const float2* uvs = nullptr;
     const float4* colors = nullptr;
     const MeshRec* meshes = nullptr;
+    size_t nodeVariantStride = 0;   // float4 units between direction-octant variants of the node array
     int nNodes = 0;
     int nTris = 0;
     int missShader = 0;

@@ -195,7 +195,6 @@ struct RayBox {
     float fix, fiy, fiz;      // invF
     float nax, nay, naz;      // addN
     float fax, fay, faz;      // addF
-    bool sx, sy, sz;          // direction negative -> near plane is max
 };
 
 __device__ __forceinline__ float rcpApprox(float x)
@@ -217,11 +216,11 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return r;
 }
 
-__device__ __forceinline__ void setupAxis(float o, float d, float& invN, float& invF, float& addN, float& addF, bool& neg)
+__device__ __forceinline__ void setupAxis(float o, float d, float& invN, float& invF, float& addN, float& addF, int& neg)
 {
     const float dc = (fabsf(d) < 1e-18f) ? copysignf(1e-18f, d) : d;
     const float inv = rcpApprox(dc);
-    neg = inv < 0.0f;
+    neg = (int)(__float_as_uint(dc) >> 31);         // direction negative -> near plane is max
     invN = inv * (1.0f - 4.76837158203125e-07f);
     invF = inv * (1.0f + 4.76837158203125e-07f);
     const float oN = o * invN, oF = o * invF;
@@ -284,13 +283,17 @@ struct Stack {
 };
 
 template <bool COUNT>
-__device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray& ray,
-                                            const float tmax, int* sStackLane, int stackStride, int* nodeCount, int* triCount)
+__device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll, size_t variantStride,
+                                            const float4* __restrict__ tris, const Ray& ray, const float tmax, int* sStackLane,
+                                            int stackStride, int* nodeCount, int* triCount)
 {
     RayBox rb;
-    setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, rb.sx);
-    setupAxis(ray.o.y, ray.d.y, rb.niy, rb.fiy, rb.nay, rb.fay, rb.sy);
-    setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, rb.sz);
+    int sx, sy, sz;
+    setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
+    setupAxis(ray.o.y, ray.d.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
+    setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
+    // node variant of this ray's direction octant: (near, far) planes are pre-selected
+    const float4* __restrict__ nodes = nodesAll + (size_t)(sx | (sy << 1) | (sz << 2)) * variantStride;
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
     Stack st;
@@ -302,14 +305,10 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodes, co
             const float4* np = nodes + 4 * (size_t)cur;
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
             if (COUNT) nc++;
-            const float tn0 = fmax3(fmaf(rb.sx ? n0.y : n0.x, rb.nix, rb.nax), fmaf(rb.sy ? n0.w : n0.z, rb.niy, rb.nay),
-                                    fmaxf(fmaf(rb.sz ? n2.y : n2.x, rb.niz, rb.naz), ray.tmin));
-            const float tf0 = fmin3(fmaf(rb.sx ? n0.x : n0.y, rb.fix, rb.fax), fmaf(rb.sy ? n0.z : n0.w, rb.fiy, rb.fay),
-                                    fminf(fmaf(rb.sz ? n2.x : n2.y, rb.fiz, rb.faz), best.t));
-            const float tn1 = fmax3(fmaf(rb.sx ? n1.y : n1.x, rb.nix, rb.nax), fmaf(rb.sy ? n1.w : n1.z, rb.niy, rb.nay),
-                                    fmaxf(fmaf(rb.sz ? n2.w : n2.z, rb.niz, rb.naz), ray.tmin));
-            const float tf1 = fmin3(fmaf(rb.sx ? n1.x : n1.y, rb.fix, rb.fax), fmaf(rb.sy ? n1.z : n1.w, rb.fiy, rb.fay),
-                                    fminf(fmaf(rb.sz ? n2.z : n2.w, rb.fiz, rb.faz), best.t));
+            const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), ray.tmin));
+            const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), best.t));
+            const float tn1 = fmax3(fmaf(n1.x, rb.nix, rb.nax), fmaf(n1.z, rb.niy, rb.nay), fmaxf(fmaf(n2.z, rb.niz, rb.naz), ray.tmin));
+            const float tf1 = fmin3(fmaf(n1.y, rb.fix, rb.fax), fmaf(n1.w, rb.fiy, rb.fay), fminf(fmaf(n2.w, rb.fiz, rb.faz), best.t));
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
             const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
             if (h0 && h1) {
@@ -413,7 +412,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
         Rng rng = rngLoad(statePtr);
         const Ray ray = ommatidialRay(p0, p1, p2, ep.pose, rng);
         rngStore(statePtr, rng);
-        const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads, nullptr, nullptr);
+        const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads, nullptr, nullptr);
         const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
         float* dst = ep.samples + 3 * (size_t)r;
         dst[0] = col.x * invS; dst[1] = col.y * invS; dst[2] = col.z * invS;          // shaders.cu:730
@@ -590,7 +589,7 @@ k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1,
         ray.o = vadd(vadd(C, vmuls(vmuls(X, dx), s0)), vmuls(vmuls(Y, dy), s1));
     }
     ray.tmin = 0.01f;
-    const Hit h = traceClosest<false>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, nullptr, nullptr);
+    const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, nullptr, nullptr);
     const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
     frame[p] = makeColor(col.x, col.y, col.z);
 }
@@ -609,7 +608,7 @@ __global__ void k_traceRays(const DeviceScene sc, const float* __restrict__ orig
     ray.d = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
     ray.tmin = tmins[i];
     int nc = 0, tc = 0;
-    const Hit h = traceClosest<true>(sc.nodes, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, &nc, &tc);
+    const Hit h = traceClosest<true>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, &nc, &tc);
     hits[2 * i] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
     hits[2 * i + 1] = make_int4(nc, tc, 0, 0);
 }

@@ -245,6 +245,7 @@ void Renderer::uploadScene()
     dscene_.colors = dColors_;
     dscene_.meshes = dMeshes_;
     dscene_.nNodes = bvh_.nNodes;
+    dscene_.nodeVariantStride = static_cast<size_t>(4) * static_cast<size_t>(bvh_.nNodes);
     dscene_.nTris = bvh_.nTris;
     dscene_.missShader = scene_.missShader;
     if (verbose)
