@@ -53,9 +53,11 @@ struct Rng {
     int flag;
     float extra;
 };
+// The state array is streamed once per frame (64 B per ray in and out): evict-first accesses keep it
+// from displacing BVH nodes in L1/L2.
 __device__ __forceinline__ Rng rngLoad(const uint4* __restrict__ p)
 {
-    const uint4 a = p[0], b = p[1];
+    const uint4 a = __ldcs(p), b = __ldcs(p + 1);
     Rng r;
     r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
     r.flag = (int)b.z; r.extra = __uint_as_float(b.w);
@@ -63,8 +65,8 @@ __device__ __forceinline__ Rng rngLoad(const uint4* __restrict__ p)
 }
 __device__ __forceinline__ void rngStore(uint4* __restrict__ p, const Rng& r)
 {
-    p[0] = make_uint4(r.d, r.v0, r.v1, r.v2);
-    p[1] = make_uint4(r.v3, r.v4, (uint32_t)r.flag, __float_as_uint(r.extra));
+    __stcs(p, make_uint4(r.d, r.v0, r.v1, r.v2));
+    __stcs(p + 1, make_uint4(r.v3, r.v4, (uint32_t)r.flag, __float_as_uint(r.extra)));
 }
 __device__ __forceinline__ uint32_t rngNext(Rng& r)
 {
@@ -314,7 +316,11 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
             if (h0 && h1) {
                 const bool firstIs0 = tn0 <= tn1;          // near child first; ties -> child 0
                 cur = firstIs0 ? r0 : r1;
-                st.push(firstIs0 ? r1 : r0);
+                const int far = firstIs0 ? r1 : r0;
+                st.push(far);
+#ifdef CR_PREFETCH_FAR
+                if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + 4 * (size_t)far));
+#endif
             } else if (h0) cur = r0;
             else if (h1) cur = r1;
             else cur = st.pop();
@@ -406,6 +412,9 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     const float invS = 1.0f / (float)(uint32_t)ep.S;
     const unsigned stride = gridDim.x * kTraceThreads;
     for (unsigned r = blockIdx.x * kTraceThreads + threadIdx.x; r < total; r += stride) {
+        if (r + stride < total) {                       // warm L2/L1 with the next ray's RNG state
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * (size_t)(r + stride)));
+        }
         const unsigned o = r / (unsigned)ep.S;
         const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
         uint4* statePtr = ep.rng + 2 * (size_t)r;
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
         const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads, nullptr, nullptr);
         const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
         float* dst = ep.samples + 3 * (size_t)r;
-        dst[0] = col.x * invS; dst[1] = col.y * invS; dst[2] = col.z * invS;          // shaders.cu:730
+        __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
         if (DUMP) {
             const unsigned s = r - o * (unsigned)ep.S;
             const size_t id = (size_t)ep.N * s + o;                                     // reference stream-id order
