@@ -1,0 +1,143 @@
+"""GPU parity at the BASELINE.json configuration sizes (cfg3/cfg4/cfg5), through the C ABI.
+
+Full-size frames cannot be brute-forced on the CPU, so these use (i) the oracle's own SAH BVH
+(independent of the product's LBVH) on the full scene and (ii) size-independent properties:
+batch == per-frame API, sharded start == sequential run, variance ~ 1/S."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+HIT4 = np.dtype([("prim", np.int32), ("t", np.float32), ("u", np.float32), ("v", np.float32)])
+
+
+@pytest.fixture(scope="module")
+def terrain(synth_dir):
+    from tools import synth
+    gltf = os.path.join(synth_dir, "terrain1m.gltf")
+    synth.write_eye(os.path.join(synth_dir, "eye10k.eye"), synth.fibonacci_eye(10000))
+    info = synth.write_terrain_gltf(gltf, triangles=1_000_000, eye_file="eye10k.eye")
+    assert info["triangles"] >= 1_000_000
+    return gltf
+
+
+def test_cfg4_million_triangle_terrain_10k_eye(lib, er, loader, oracle, terrain):
+    """Headline workload geometry: 1M-triangle terrain, 10k-ommatidia eye.  One S=8 frame (80k rays):
+    rays, hit ids, (t,u,v), per-ommatidium RGB and the frame are bit-exact vs the oracle, whose hits
+    come from its own binned-SAH BVH over the same million triangles."""
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.crDebugGetTriangleCount() >= 1_000_000
+    assert lib.gotoCameraByName(b"compound-cam")
+    N, S = 10000, 8
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    sc, sh, ocam = load_oracle_scene(loader, oracle, terrain, "compound-cam")
+    T = lib.crDebugGetTriangleCount()
+    tris = np.zeros((T, 9), np.float32)
+    lib.crDebugCopyTriangles(tris.ctypes.data)
+    assert np.array_equal(tris.view(np.uint32), sc.tris.view(np.uint32))
+    eye = oracle.CompoundEyeOracle(sh, ocam.ommatidia, oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    lib.crDebugSetRayDump(True)
+    for frame in range(2):
+        lib.renderFrame()
+        eye.render_frame(method="bvh")
+        o = np.zeros((N * S, 3), np.float32); d = np.zeros((N * S, 3), np.float32); h = np.zeros(N * S, HIT4)
+        assert lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data) == N * S
+        assert np.array_equal(d.view(np.uint32), eye.last["dirs"].view(np.uint32))
+        assert np.array_equal(h["prim"], eye.last["hits"]["prim"])
+        hit = h["prim"] >= 0
+        assert 0.3 < hit.mean() < 0.7
+        assert np.array_equal(h["t"][hit].view(np.uint32), eye.last["hits"]["t"][hit].view(np.uint32))
+        assert np.array_equal(er.getOmmatidialData(lib).view(np.uint32), eye.last["summed"].view(np.uint32))
+        assert np.array_equal(er.getFrame(lib, N, 1), eye.frame)
+    lib.crDebugSetRayDump(False)
+    # the device BVH traversed by the oracle's instrumented loop gives the same hits (roofline counters)
+    nn = lib.crDebugGetBvhNodeCount()
+    nodes = np.zeros((nn, 16), np.float32); dtris = np.zeros((T, 12), np.float32)
+    lib.crDebugCopyBvh(nodes.ctypes.data, dtris.ctypes.data)
+    hits2, cnt = oracle.trace_device_bvh(nodes, dtris, o, d, np.zeros(N * S, np.float32))
+    assert np.array_equal(hits2["prim"], h["prim"]) and cnt[0] / (N * S) < 40
+
+
+def test_cfg4_full_sample_count_properties(lib, er, terrain):
+    """S=1024 on the headline workload (10.24M rays/frame): the batch path, the per-frame ABI and a
+    restarted (sharded) run produce byte-identical rows."""
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N = 10000
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(1024)
+    pose = np.zeros(12, np.float32)
+    lib.crDebugCopyCameraPose(pose.ctypes.data)
+    pos = pose[:3] + np.array([[0, 0, 0], [1, 0.5, -2], [-3, 1, 0.5], [0.2, 2, 4]], np.float32)
+    poses = er.make_poses(pos, x=pose[3:6], y=pose[6:9], z=pose[9:12])
+    rows, _ = er.renderPoseBatch(lib, poses)
+    lib.setCurrentEyeSamplesPerOmmatidium(1024)                      # reset streams, then frame by frame
+    for p in range(4):
+        lib.setCameraPosition(*[float(v) for v in pos[p]])
+        lib.renderFrame()
+        assert np.array_equal(er.getFrame(lib, N, 1)[0], rows[p]), f"frame {p}"
+    lib.crSetFirstFrame(2)
+    rows2, _ = er.renderPoseBatch(lib, poses[2:])
+    lib.crSetFirstFrame(0)
+    assert np.array_equal(rows2, rows[2:])
+    assert rows[:, :, :3].std() > 5 and (rows[:, :, 3] == 255).all()
+
+
+def test_cfg3_variance_falls_with_samples(lib, er, synth_dir):
+    """minimumSampleRateFinder-style statistic (data/tools/minimumSampleRateFinder.py:36-47): the
+    frame-to-frame SD of an ommatidium's output falls ~ 1/sqrt(S).  12-ommatidia 1-steradian eye."""
+    from tools import synth
+    gltf = os.path.join(synth_dir, "terrain_small.gltf")
+    synth.write_eye(os.path.join(synth_dir, "ico.eye"), synth.fibonacci_eye(12))
+    synth.write_terrain_gltf(gltf, triangles=20000, eye_file="ico.eye")
+    lib.loadGlTFscene(gltf.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    er.setOmmatidiaFromOmmatidiumList(lib, er.getIcoOmmatidia())
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    er.setRenderSize(lib, 12, 1)
+    sds = {}
+    for S in (16, 256):
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
+        lib.renderFrame()
+        vals = []
+        for _ in range(200):
+            lib.renderFrame()
+            vals.append(er.getOmmatidialData(lib))
+        sds[S] = np.stack(vals).std(axis=0).mean()
+    ratio = sds[16] / sds[256]
+    assert 3.0 < ratio < 5.4, (sds, ratio)                           # expected sqrt(256/16) = 4
+
+
+def test_cfg5_heterogeneous_eye_pose_batch(lib, er, loader, oracle, ref_data):
+    """env_2.gltf + AM_60185-real geometry with log-uniform acceptance angles (numpy rng 5), random
+    positions in the 50 mm cube (rng 0): batch rows == oracle frames within the texture tolerance,
+    hit ids exact."""
+    from tools import synth
+    path = os.path.join(ref_data, "sim-environment", "env_2.gltf")
+    lib.loadGlTFscene(path.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    sc, sh, ocam = load_oracle_scene(loader, oracle, path, "compound-cam")
+    omm = synth.heterogeneous_eye(ocam.ommatidia)
+    assert len(omm) == 6374 and omm[:, 6].min() >= 0.02 and omm[:, 6].max() <= 0.35
+    er.setOmmatidiaFromArray(lib, omm)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N, S, P = len(omm), 16, 3
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    pos = np.random.default_rng(0).uniform(-25, 25, (P, 3)).astype(np.float32)
+    poses = er.make_poses(pos, x=ocam.x_axis, y=ocam.y_axis, z=ocam.z_axis)
+    rows, _ = er.renderPoseBatch(lib, poses)
+    eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    for p in range(P):
+        eye.pose = oracle.make_pose(pos[p], ocam.x_axis, ocam.y_axis, ocam.z_axis)
+        eye.render_frame(method="bvh")
+        diff = np.abs(rows[p].astype(np.int32) - eye.frame[0].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.02, (p, diff.max(), (diff > 0).mean())
