@@ -51,7 +51,7 @@ struct DeviceScene {
     int missShader = 0;
 };
 
-struct DevicePose {
+struct alignas(16) DevicePose {
     float px, py, pz;
     float xx, xy, xz;
     float yx, yy, yz;
@@ -69,6 +69,8 @@ struct EyeParams {
     int4* dumpHits = nullptr;     // (prim, t bits, u bits, v bits)
     int N = 0;
     int S = 0;
+    int nFrames = 1;              // frames (poses) covered by one launch
+    const DevicePose* poses = nullptr;   // device array [nFrames]; nullptr: use `pose`
     DevicePose pose;
 };
 

@@ -404,43 +404,70 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 // colour/S (shaders.cu:730) goes to the [o][s] sample buffer and K1b sums it IN SAMPLE ORDER,
 // which is exactly the reference's sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347).
 // ------------------------------------------------------------------------------------------
-template <bool DUMP>
+template <bool DUMP, bool MULTI>
 __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCompound(const DeviceScene sc, const EyeParams ep)
 {
     __shared__ int sStack[kSmemStack][kTraceThreads];
+    __shared__ uint4 sRng[MULTI ? 2 : 1][MULTI ? kTraceThreads : 1];   // RNG state parked here while a ray is traced (batches)
     const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
     const float invS = 1.0f / (float)(uint32_t)ep.S;
     const unsigned stride = gridDim.x * kTraceThreads;
+    const int F = MULTI ? ep.nFrames : 1;
     for (unsigned r = blockIdx.x * kTraceThreads + threadIdx.x; r < total; r += stride) {
-        if (r + stride < total) {                       // warm L2/L1 with the next ray's RNG state
+        if (r + stride < total) {                       // warm L2 with the next ray's RNG state
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * (size_t)(r + stride)));
         }
         const unsigned o = r / (unsigned)ep.S;
-        const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
         uint4* statePtr = ep.rng + 2 * (size_t)r;
         Rng rng = rngLoad(statePtr);
-        const Ray ray = ommatidialRay(p0, p1, p2, ep.pose, rng);
-        rngStore(statePtr, rng);
-        const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads, nullptr, nullptr);
-        const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
-        float* dst = ep.samples + 3 * (size_t)r;
-        __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
-        if (DUMP) {
-            const unsigned s = r - o * (unsigned)ep.S;
-            const size_t id = (size_t)ep.N * s + o;                                     // reference stream-id order
-            ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
-            ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
-            ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
+        // Consecutive frames of one sample stream are processed back to back by the same lane: the
+        // state is loaded and stored once per batch, and one launch covers F frames (poses).
+        for (int f = 0; f < F; f++) {
+            DevicePose pose = ep.pose;
+            if (MULTI) {
+                const float4* pp = reinterpret_cast<const float4*>(ep.poses + f);
+                const float4 a = __ldg(pp), b = __ldg(pp + 1), c = __ldg(pp + 2);
+                pose.px = a.x; pose.py = a.y; pose.pz = a.z; pose.xx = a.w;
+                pose.xy = b.x; pose.xz = b.y; pose.yx = b.z; pose.yy = b.w;
+                pose.yz = c.x; pose.zx = c.y; pose.zy = c.z; pose.zz = c.w;
+            }
+            const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
+            const Ray ray = ommatidialRay(p0, p1, p2, pose, rng);
+            if (MULTI) {   // park the state in shared memory: its 8 registers are dead while the ray is traced
+                sRng[0][threadIdx.x] = make_uint4(rng.d, rng.v0, rng.v1, rng.v2);
+                sRng[1][threadIdx.x] = make_uint4(rng.v3, rng.v4, (uint32_t)rng.flag, __float_as_uint(rng.extra));
+            } else {
+                rngStore(statePtr, rng);
+            }
+            const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x],
+                                              kTraceThreads, nullptr, nullptr);
+            const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
+            float* dst = ep.samples + 3 * ((size_t)f * total + r);
+            __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
+            if (MULTI) {
+                const uint4 a = sRng[0][threadIdx.x], b = sRng[1][threadIdx.x];
+                rng.d = a.x; rng.v0 = a.y; rng.v1 = a.z; rng.v2 = a.w; rng.v3 = b.x; rng.v4 = b.y;
+                rng.flag = (int)b.z; rng.extra = __uint_as_float(b.w);
+            }
+            if (DUMP) {
+                const unsigned s = r - o * (unsigned)ep.S;
+                const size_t id = (size_t)ep.N * s + o;                                 // reference stream-id order
+                ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
+                ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
+                ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
+            }
         }
+        if (MULTI) rngStore(statePtr, rng);
     }
 }
 
-// K1b: summed[o].ch = ((0 + c[o][0]) + c[o][1]) + ... + c[o][S-1], one thread per (ommatidium, channel).
-__global__ void k_sumSamples(const float* __restrict__ samples, int N, int S, float4* __restrict__ summed)
+// K1b: summed[f][o].ch = ((0 + c[f][o][0]) + c[f][o][1]) + ... + c[f][o][S-1], one thread per
+// (frame, ommatidium, channel): the reference's sequential fp32 order (shaders.cu:341-347).
+__global__ void k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 3 * N) return;
-    const int o = k / 3, ch = k - 3 * o;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3ll * NF) return;
+    const int o = (int)(k / 3), ch = (int)(k - 3ll * o);
     const float* src = samples + 3 * (size_t)o * S + ch;
     float sum = 0.0f;
     int s = 0;
@@ -667,15 +694,17 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     if (total <= 0) return;
     const long long need = (total + kTraceThreads - 1) / kTraceThreads;
     const int grid = (int)(need < gridBlocks ? need : gridBlocks);
-    if (eye.dumpHits) k_traceCompound<true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
-    else k_traceCompound<false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
-    k_sumSamples<<<(unsigned)((3 * eye.N + 127) / 128), 128, 0, stream>>>(eye.samples, eye.N, eye.S, eye.summed);
+    if (eye.dumpHits) k_traceCompound<true, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    else if (eye.poses) k_traceCompound<false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    const long long nf = (long long)eye.N * eye.nFrames;
+    k_sumSamples<<<(unsigned)((3 * nf + 127) / 128), 128, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed);
 }
 
 int traceKernelOccupancy()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false>, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false, true>, kTraceThreads, 0);
     return n > 0 ? n : 1;
 }
 

@@ -108,6 +108,8 @@ void Renderer::freeCompound(CompoundState& cs)
 {
     dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
+    dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses);
+    cs.batchSampleCap = cs.batchSummedCap = cs.batchPoseCap = 0;
     cs.dumpCap = 0;
     cs.rngN = cs.rngS = 0;
     cs.mapMode = -2;
@@ -381,6 +383,23 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
     cs.frameIndex++;
 }
 
+void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed)
+{
+    EyeParams ep;
+    ep.pre = cs.dPre;
+    ep.rng = cs.dRng;
+    ep.summed = dSummed;
+    ep.samples = dSamples;
+    ep.N = cs.N;
+    ep.S = cs.S;
+    ep.nFrames = nFrames;
+    ep.poses = dPoses;
+    const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
+    launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
+    launches_ += 2;
+    cs.frameIndex += static_cast<uint64_t>(nFrames);
+}
+
 void Renderer::project(CompoundState& cs, const HostCamera& cam)
 {
     const int mode = projectionFromName(cam.projection);
@@ -532,7 +551,30 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
     uchar4* dOut = static_cast<uchar4*>(outDevice);
     uchar4* dTmp = nullptr;
     if (!dOut) { dTmp = dallocT<uchar4>(N * count); dOut = dTmp; }
-    CR_CUDA(cudaEventRecord(evA_, stream_));
+    // frames per launch: bounded by a sample-buffer budget (12 B per ray per frame)
+    const size_t raysPerFrame = N * static_cast<size_t>(cs.S);
+    size_t budget = size_t(1) << 30;
+    if (const char* env = getenv("CR_BATCH_BYTES")) budget = static_cast<size_t>(atoll(env));
+    size_t F = std::max<size_t>(1, std::min<size_t>(count, budget / std::max<size_t>(1, raysPerFrame * 12)));
+    if (const char* env = getenv("CR_BATCH_FRAMES")) F = std::max<size_t>(1, std::min<size_t>(count, static_cast<size_t>(atoll(env))));
+    if (dumpRays) F = 1;
+    if (cs.batchSampleCap < F * raysPerFrame * 3) {
+        dfree(cs.dBatchSamples);
+        cs.dBatchSamples = dallocT<float>(F * raysPerFrame * 3);
+        cs.batchSampleCap = F * raysPerFrame * 3;
+    }
+    if (cs.batchSummedCap < F * N) {
+        dfree(cs.dBatchSummed);
+        cs.dBatchSummed = dallocT<float4>(F * N);
+        CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
+        cs.batchSummedCap = F * N;
+    }
+    if (cs.batchPoseCap < count) {
+        dfree(cs.dBatchPoses);
+        cs.dBatchPoses = dallocT<DevicePose>(count);
+        cs.batchPoseCap = count;
+    }
+    std::vector<DevicePose> hPoses(count);
     for (size_t p = 0; p < count; p++) {
         Pose pose;
         const float* q = poses12 + 12 * p;
@@ -540,8 +582,22 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         pose.ax = {q[3], q[4], q[5]};
         pose.ay = {q[6], q[7], q[8]};
         pose.az = {q[9], q[10], q[11]};
-        launchCompound(cs, cam, pose);
-        launchPackRow(cs.dSummed, cs.N, dOut + p * N, stream_);
+        hPoses[p] = toDevicePose(pose);
+    }
+    CR_CUDA(cudaMemcpyAsync(cs.dBatchPoses, hPoses.data(), sizeof(DevicePose) * count, cudaMemcpyHostToDevice, stream_));
+    CR_CUDA(cudaEventRecord(evA_, stream_));
+    for (size_t p0 = 0; p0 < count; p0 += F) {
+        const size_t Fc = std::min(F, count - p0);
+        if (dumpRays) {                       // the per-ray dump lives in the single-frame path
+            Pose pose;
+            const float* q = poses12 + 12 * p0;
+            pose.pos = {q[0], q[1], q[2]}; pose.ax = {q[3], q[4], q[5]}; pose.ay = {q[6], q[7], q[8]}; pose.az = {q[9], q[10], q[11]};
+            launchCompound(cs, cam, pose);
+            launchPackRow(cs.dSummed, cs.N, dOut + p0 * N, stream_);
+        } else {
+            launchCompoundBatch(cs, cs.dBatchPoses + p0, static_cast<int>(Fc), cs.dBatchSamples, cs.dBatchSummed);
+            launchPackRow(cs.dBatchSummed, static_cast<int>(Fc * N), dOut + p0 * N, stream_);
+        }
         launches_++;
     }
     CR_CUDA(cudaEventRecord(evB_, stream_));

@@ -32,6 +32,9 @@ struct CompoundState {                 // device side of one CompoundEye camera
     bool randomsConfigured = false;    // cameras/CompoundEyeDataTypes.h:12
     uint64_t frameIndex = 0;           // frames rendered since the streams were (re)initialised
     uint64_t firstFrame = 0;           // frame offset applied at the next stream initialisation
+    // multi-frame batch buffers (crRenderPoseBatch)
+    float* dBatchSamples = nullptr; float4* dBatchSummed = nullptr; DevicePose* dBatchPoses = nullptr;
+    size_t batchSampleCap = 0, batchSummedCap = 0, batchPoseCap = 0;
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; size_t dumpCap = 0;
 };
@@ -91,6 +94,7 @@ private:
     CompoundState& compoundState(size_t camIdx);
     void prepareCompound(CompoundState& cs, HostCamera& cam);
     void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose);
+    void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed);
     void project(CompoundState& cs, const HostCamera& cam);
     void ensureFrame();
     void freeCompound(CompoundState& cs);
