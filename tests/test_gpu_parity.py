@@ -316,3 +316,60 @@ def test_ordinary_cameras(lib, er, ref_data, loader, oracle):
         rgb = oracle.shade(sh, hits, d)
         ref = oracle.make_color(rgb).reshape(64, 96, 4)
         assert np.array_equal(fr, ref), cam.name
+
+
+def _write_tri_scene(path, n_tris, background="simple_sky"):
+    """n_tris random triangles around the origin (0 = empty scene) + a compound camera at the origin."""
+    import base64
+    import json
+    rng = np.random.default_rng(n_tris + 11)
+    nodes = [{"camera": 0, "name": "cam"}]
+    gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0], "extras": {"background-shader": background}}], "nodes": nodes,
+            "cameras": [{"name": "cam", "type": "perspective", "perspective": {"yfov": 0.5, "znear": 0.1},
+                         "extras": {"compound-eye": True, "compound-projection": "single_dimension_fast", "compound-structure": "e.eye"}}]}
+    if n_tris:
+        c = rng.uniform(-3, 3, (n_tris, 1, 3))
+        v = (c + rng.uniform(-1.5, 1.5, (n_tris, 3, 3))).astype(np.float32).reshape(-1, 3)
+        col = rng.uniform(0, 1, (len(v), 4)).astype(np.float32)
+        blob = v.tobytes() + col.tobytes()
+        gltf["scenes"][0]["nodes"].append(1)
+        nodes.append({"mesh": 0, "name": "soup"})
+        gltf["meshes"] = [{"name": "soup", "primitives": [{"attributes": {"POSITION": 0, "COLOR_0": 1}}]}]      # non-indexed
+        gltf["accessors"] = [{"bufferView": 0, "componentType": 5126, "count": len(v), "type": "VEC3",
+                              "min": v.min(0).tolist(), "max": v.max(0).tolist()},
+                             {"bufferView": 1, "componentType": 5126, "count": len(v), "type": "VEC4"}]
+        gltf["bufferViews"] = [{"buffer": 0, "byteOffset": 0, "byteLength": v.nbytes},
+                               {"buffer": 0, "byteOffset": v.nbytes, "byteLength": col.nbytes}]
+        gltf["buffers"] = [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]
+    with open(path, "w") as f:
+        json.dump(gltf, f)
+
+
+@pytest.mark.parametrize("n_tris", [0, 1, 2, 3, 4, 5, 9])
+def test_tiny_and_empty_scenes(lib, er, loader, oracle, tmp_path, n_tris):
+    """Builder edge cases: empty scene (every ray misses), a single triangle, scenes that fit one
+    leaf (n <= 4), the first real hierarchies; non-indexed geometry with float COLOR_0."""
+    from tools import synth
+    gltf = str(tmp_path / f"t{n_tris}.gltf")
+    synth.write_eye(str(tmp_path / "e.eye"), synth.fibonacci_eye(300, radius=0.05, acceptance=0.3))
+    _write_tri_scene(gltf, n_tris, background="simple_sky" if n_tris % 2 == 0 else "default_background")
+    lib.loadGlTFscene(gltf.encode())
+    assert lib.crDebugGetTriangleCount() == n_tris
+    assert lib.gotoCameraByName(b"cam")
+    N, S = 300, 5
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    sc, sh, ocam = load_oracle_scene(loader, oracle, gltf, "cam")
+    eye = oracle.CompoundEyeOracle(sh, ocam.ommatidia, oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    lib.crDebugSetRayDump(True)
+    lib.renderFrame(); eye.render_frame(method="brute")
+    o, d, h = _product_rays(lib, N * S)
+    lib.crDebugSetRayDump(False)
+    assert np.array_equal(h["prim"], eye.last["hits"]["prim"])
+    if n_tris == 0:
+        assert (h["prim"] == -1).all()
+    else:
+        assert (h["prim"] >= 0).any()
+    assert np.array_equal(er.getOmmatidialData(lib).view(np.uint32), eye.last["summed"].view(np.uint32))
+    assert np.array_equal(_frame(er, lib, N, 1), eye.frame)
