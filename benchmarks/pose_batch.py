@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""benchmarks/pose_batch.py -- BASELINE config 5: pose-batched rendering of the position-estimation
+toy experiment (env_2.gltf, AM_60185-real eye geometry with heterogeneous acceptance angles,
+positions uniform in the 50 mm cube, numpy default_rng(0)), 1..8 GPUs, NCCL allgather of the rows.
+
+  python benchmarks/pose_batch.py [--poses 512] [--samples 64]
+  torchrun --nproc-per-node N benchmarks/pose_batch.py ...
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "compound-ray_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "benchmarks")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--poses", type=int, default=512)
+    ap.add_argument("--samples", type=int, default=64)
+    args = ap.parse_args()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    import eye_renderer as er
+    import sharding
+    import speed_test
+    from tools import synth
+    data = speed_test.fixtures()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = er.load_library(device=local)
+    lib.setVerbosity(False)
+    lib.loadGlTFscene(os.path.join(data, "sim-environment", "env_2.gltf").encode())
+    lib.gotoCameraByName(b"compound-cam")
+    base = np.array([[*o.position, *o.direction, o.acceptanceAngle, o.focalpointOffset] for o in
+                     er.readEyeFile(os.path.join(data, "sim-environment", "eyes", "AM_60185-real.eye"))], np.float32)
+    omm = synth.heterogeneous_eye(base)
+    er.setOmmatidiaFromArray(lib, omm)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N, S, P = len(omm), args.samples, args.poses
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    pose = np.zeros(12, np.float32)
+    lib.crDebugCopyCameraPose(pose.ctypes.data)
+    pos = np.random.default_rng(0).uniform(-25, 25, (P, 3)).astype(np.float32)
+    lo, hi = sharding.pose_block(rank, world, P)
+    poses = er.make_poses(pos[lo:hi], x=pose[3:6], y=pose[6:9], z=pose[9:12])
+    lib.crSetFirstFrame(lo)
+    er.renderPoseBatch(lib, poses[:min(8, len(poses))])                      # warm-up (then rewind the streams)
+    lib.crSetFirstFrame(lo)
+    if world > 1:
+        blk = sharding.padded_block_size(world, P)
+        send = torch.zeros((blk, N, 4), dtype=torch.uint8, device="cuda")
+        gathered = torch.empty((world * blk, N, 4), dtype=torch.uint8, device="cuda")
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        er.renderPoseBatch(lib, poses, out_device_ptr=send.data_ptr())
+        dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        checksum = int(sharding.unpad(gathered, world, P).to(torch.int64).sum().item())
+    else:
+        t0 = time.perf_counter()
+        rows, _ = er.renderPoseBatch(lib, poses)
+        dt = time.perf_counter() - t0
+        checksum = int(rows.astype(np.int64).sum())
+    if rank == 0:
+        out = {"benchmark": "pose batch (BASELINE config 5)", "n_gpus": world, "poses": P, "ommatidia": N, "samples": S,
+               "seconds": dt, "poses_per_sec": P / dt, "rays_per_sec": P * N * S / dt, "ommatidia_frames_per_sec": P * N / dt,
+               "checksum": checksum, "timing": "host wall clock incl. pose upload, render, allgather / D2H; max over ranks"}
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

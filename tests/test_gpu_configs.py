@@ -141,3 +141,40 @@ def test_cfg5_heterogeneous_eye_pose_batch(lib, er, loader, oracle, ref_data):
         eye.render_frame(method="bvh")
         diff = np.abs(rows[p].astype(np.int32) - eye.frame[0].astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() < 0.02, (p, diff.max(), (diff > 0).mean())
+
+
+def test_batched_iterators_match_the_reference_loop(lib, er, ref_data):
+    """compound-ray_b200/iterators.py vs the loop of compoundRayIterators.py:84-102 / :121-143
+    (setCameraPosition + renderFrame + getFramePointer per item): identical images and positions."""
+    import iterators
+    scene = os.path.join(ref_data, "sim-environment", "env_2.gltf")
+    eye = os.path.join(ref_data, "sim-environment", "eyes", "AM_60185-real.eye")
+    S = 24
+    # reference-style loop through the plain ABI
+    lib.loadGlTFscene(scene.encode())
+    lib.gotoCameraByName(b"compound-cam")
+    cfg = er.readEyeFile(eye)
+    er.setOmmatidiaFromOmmatidiumList(lib, cfg)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    er.setRenderSize(lib, len(cfg), 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    np.random.seed(123)
+    want = []
+    for _ in range(7):
+        rel = (np.random.random(3) * 2 - 1) * 25.0
+        lib.setCameraPosition(*[float(v) for v in rel])
+        lib.renderFrame()
+        want.append((np.copy(lib.getFramePointer()[:, :, :3]), rel))
+    np.random.seed(123)
+    it = iter(iterators.RandomCubeIterator(eye, scenePath=scene, samples=S, blockSize=4))
+    for k in range(7):
+        img, pos = next(it)
+        assert img.shape == (1, len(cfg), 3)
+        assert np.array_equal(img.numpy(), want[k][0].astype(np.float32)), k
+        assert np.allclose(pos.numpy(), want[k][1].astype(np.float32))
+    uit = iter(iterators.UniformCubeIterator(eye, scenePath=scene, samples=S, blockSize=3, samplingSize=2, cubeSize=10))
+    seen = [next(uit) for _ in range(9)]                       # wraps after 8 lattice points
+    assert [tuple(c) for _, _, c in seen[:8]] == [(x, y, z) for z in (0, 1) for y in (0, 1) for x in (0, 1)]
+    assert tuple(seen[8][2]) == (0, 0, 0) and seen[0][0].shape == (1, len(cfg))
+    gap = 10 / 3
+    assert np.allclose(seen[3][1].numpy(), np.array([1, 1, 0]) * gap - gap)
