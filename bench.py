@@ -311,6 +311,8 @@ def main():
         out_host, host_ms = er.renderPoseBatch(lib, timed)      # D2H of K*N*4 bytes happens AFTER the event pair
         dev_ms = lib.crGetLastTraceMs()
     launches_timed = lib.crGetLaunchCount() - launches1
+    lib.crGetLastBatchFrames.restype = C.c_int
+    frames_per_launch = lib.crGetLastBatchFrames()
     rays_per_step = N * S
     value = world * K * rays_per_step / (dev_ms * 1e-3)
 
@@ -336,26 +338,32 @@ def main():
 
         # -------------------------------------------------------------- roofline of the dominant kernel (K1)
         n_node, n_tri, hit_frac = traversal_counters(lib, er)
-        bytes_per_ray = 64.0 * n_node + 48.0 * n_tri + 64.0 + 48.0 / S
+        lib.crGetLastBatchFrames.restype = C.c_int
+        F = max(1, int(frames_per_launch))
+        # per ray: node + triangle fetches, RNG state read+write once per F-frame launch, 12 B sample write +
+        # 12 B read by the ordered sum, ommatidium row + result amortised over S
+        bytes_per_ray = 64.0 * n_node + 48.0 * n_tri + 64.0 / F + 24.0 + 48.0 / S
         peak, peak_src = measured_peak_gbs()
         achieved = (value / world) * bytes_per_ray / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch") if tj.get("frames_per_launch") == F else None
             except Exception:
                 traffic = None
-        dram_gbs = (traffic / (dev_ms / K * 1e-3) / 1e9) if traffic else None     # measured DRAM bytes (ncu) over the live launch time
+        dram_gbs = (traffic / (dev_ms / K * F * 1e-3) / 1e9) if traffic else None # measured DRAM bytes (ncu) over the live launch time
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "dram_achieved_gbs": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
-                    "kernel": "k_traceCompound", "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                    "kernel": "k_traceCompound<false,true>", "frames_per_launch": F,
+                    "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_step * F, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
                     "hit_fraction": hit_frac, "peak_source": peak_src,
-                    "note": "achieved = SURVEY 8(d) algorithmic bytes (64*nodes + 48*tris + 64 RNG r+w + 48/S per ray) / time. The BVH "
+                    "note": "achieved = SURVEY 8(d) algorithmic bytes (64*nodes + 48*tris + 64/F RNG r+w + 24 sample w+r + 48/S per ray) / time. The BVH "
                             "bytes are L1/L2 hits (one viewpoint per frame), so frac exceeds 1: the kernel is NOT HBM-bound. "
-                            "dram_* = ncu-measured DRAM bytes per single-frame launch (RNG state + samples) / time: the true HBM "
+                            "dram_* = ncu-measured DRAM bytes per launch (RNG state + samples) / live launch time: the true HBM "
                             "utilisation. ncu: issue slots 65% busy, 23/32 lanes active, top stall long-scoreboard (node fetch "
-                            "latency) -- see profiles/r01_v3_k1_ncu_summary.txt"}
+                            "latency) -- see profiles/r01_final_k1_ncu_summary.txt"}
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(gltf, S)
         out = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -207,6 +207,7 @@ void crSetFirstFrame(uint64_t frame)
 double crGetLastTraceMs(void) { return renderer().lastTraceMs(); }
 unsigned long long crGetLaunchCount(void) { return renderer().launchCount(); }
 double crGetBvhBuildMs(void) { return renderer().bvhBuildMs(); }
+int crGetLastBatchFrames(void) { return renderer().lastBatchFrames(); }
 
 // ---------------------------------------------------------------- parity / debug access
 size_t crDebugGetTriangleCount(void) { return renderer().scene().triangleCount(); }

@@ -558,6 +558,7 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
     size_t F = std::max<size_t>(1, std::min<size_t>(count, budget / std::max<size_t>(1, raysPerFrame * 12)));
     if (const char* env = getenv("CR_BATCH_FRAMES")) F = std::max<size_t>(1, std::min<size_t>(count, static_cast<size_t>(atoll(env))));
     if (dumpRays) F = 1;
+    lastBatchFrames_ = static_cast<int>(F);
     if (cs.batchSampleCap < F * raysPerFrame * 3) {
         dfree(cs.dBatchSamples);
         cs.dBatchSamples = dallocT<float>(F * raysPerFrame * 3);

@@ -77,6 +77,7 @@ public:
     double lastTraceMs() const { return lastTraceMs_; }
     unsigned long long launchCount() const { return launches_; }
     double bvhBuildMs() const { return bvh_.buildMs; }
+    int lastBatchFrames() const { return lastBatchFrames_; }
 
     // debug / parity access
     void debugCopyBvh(float* nodes, float* tris);
@@ -131,6 +132,7 @@ private:
     int frameW_ = 0, frameH_ = 0;
 
     double lastTraceMs_ = 0.0;
+    int lastBatchFrames_ = 1;
     unsigned long long launches_ = 0;
 };
 

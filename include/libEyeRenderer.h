@@ -110,6 +110,8 @@ double crGetLastTraceMs(void);
 unsigned long long crGetLaunchCount(void);
 /* Build time of the BVH of the loaded scene, milliseconds. */
 double crGetBvhBuildMs(void);
+/* Frames covered by each trace launch of the last crRenderPoseBatch call. */
+int crGetLastBatchFrames(void);
 
 /* ---- parity / debug access (used by tests and the roofline counters only) ---- */
 size_t crDebugGetTriangleCount(void);
