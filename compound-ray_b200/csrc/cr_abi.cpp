@@ -310,6 +310,12 @@ void crDebugCopyProjectionMap(uint32_t* out)
     renderer().debugCopyProjectionMap(out);
     CR_GUARD_END()
 }
+void crDebugSampleTexture(int index, const float* uv2, int n, float* outRgba4)
+{
+    CR_GUARD_BEGIN
+    renderer().debugSampleTexture(index, uv2, n, outRgba4);
+    CR_GUARD_END()
+}
 void crDebugEvalMath(int fn, const float* a, const float* b, float* out, int n)
 {
     CR_GUARD_BEGIN

@@ -110,6 +110,7 @@ void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float
                   int W, int H, cudaStream_t stream);
 void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,
                      cudaStream_t stream);
+void launchSampleTexture(unsigned long long tex, const float* uv, int n, float4* out, cudaStream_t stream);
 void launchEvalMath(int fn, const float* a, const float* b, float* out, int n, cudaStream_t stream);
 int traceKernelOccupancy();   // resident CTAs per SM for the compound trace kernel
 

@@ -649,6 +649,13 @@ __global__ void k_traceRays(const DeviceScene sc, const float* __restrict__ orig
     hits[2 * i + 1] = make_int4(nc, tc, 0, 0);
 }
 
+__global__ void k_sampleTexture(unsigned long long tex, const float* __restrict__ uv, int n, float4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = tex2D<float4>((cudaTextureObject_t)tex, uv[2 * i], uv[2 * i + 1]);
+}
+
 __global__ void k_evalMath(int fn, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -757,6 +764,12 @@ void launchTraceRays(const DeviceScene& sc, const float* origins, const float* d
 {
     if (n <= 0) return;
     k_traceRays<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, origins, dirs, tmins, n, hits);
+}
+
+void launchSampleTexture(unsigned long long tex, const float* uv, int n, float4* out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_sampleTexture<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tex, uv, n, out);
 }
 
 void launchEvalMath(int fn, const float* a, const float* b, float* out, int n, cudaStream_t stream)

@@ -677,6 +677,23 @@ void Renderer::debugCopyProjectionMap(uint32_t* out)
     CR_CUDA(cudaMemcpy(out, cs.dMap, sizeof(uint32_t) * static_cast<size_t>(cs.mapW) * static_cast<size_t>(cs.mapH), cudaMemcpyDeviceToHost));
 }
 
+void Renderer::debugSampleTexture(int index, const float* uv, int n, float* out4)
+{
+    ensureDevice();
+    if (!loaded_) throw std::runtime_error("no scene loaded");
+    if (!dscene_.nodes) uploadScene();
+    if (index < 0 || static_cast<size_t>(index) >= texObjects_.size()) throw std::runtime_error("texture index out of range");
+    float* dUv = dallocT<float>(2 * static_cast<size_t>(n));
+    float4* dOut = dallocT<float4>(static_cast<size_t>(n));
+    CR_CUDA(cudaMemcpyAsync(dUv, uv, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, stream_));
+    launchSampleTexture(static_cast<unsigned long long>(texObjects_[static_cast<size_t>(index)]), dUv, n, dOut, stream_);
+    launches_++;
+    CR_CUDA(cudaMemcpyAsync(out4, dOut, sizeof(float4) * n, cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    CR_CUDA(cudaGetLastError());
+    dfree(dUv); dfree(dOut);
+}
+
 void Renderer::debugEvalMath(int fn, const float* a, const float* b, float* out, int n)
 {
     ensureDevice();

@@ -86,6 +86,7 @@ public:
     size_t debugCopyLastRays(float* origins, float* dirs, int32_t* hits4);
     void debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8);
     void debugCopyProjectionMap(uint32_t* out);
+    void debugSampleTexture(int index, const float* uv, int n, float* out4);
     void debugEvalMath(int fn, const float* a, const float* b, float* out, int n);
     void ensureDevice();
 

@@ -128,6 +128,7 @@ def configureFunctions(eyeRenderer):
     r.crDebugCopyRngStates.argtypes = [vp]
     r.crDebugTraceRays.argtypes = [vp, vp, vp, C.c_int, vp]
     r.crDebugCopyProjectionMap.argtypes = [vp]
+    r.crDebugSampleTexture.argtypes = [C.c_int, vp, C.c_int, vp]
     r.crDebugEvalMath.argtypes = [C.c_int, vp, vp, vp, C.c_int]
 
 

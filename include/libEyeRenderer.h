@@ -136,6 +136,7 @@ size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* s
 void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */
 void crDebugTraceRays(const float* origins3, const float* dirs3, const float* tmins, int n, int32_t* hits8);
 void crDebugCopyProjectionMap(uint32_t* out);    /* W*H ommatidium indices of the cached map */
+void crDebugSampleTexture(int index, const float* uv2, int n, float* outRgba4);  /* hardware tex2D at n (u,v) */
 void crDebugEvalMath(int fn, const float* a, const float* b, float* out, int n);
 
 #ifdef __cplusplus
