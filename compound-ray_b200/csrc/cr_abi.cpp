@@ -263,6 +263,18 @@ void crDebugCopyOmmatidia(float* out8)
     const auto& o = renderer().camera().ommatidia;
     if (!o.empty()) memcpy(out8, o.data(), sizeof(cr::Ommatidium) * o.size());
 }
+static cr::ImageRGBA8 g_debugImage;
+bool crDebugDecodeImageFile(const char* path, int* w, int* h)
+{
+    CR_GUARD_BEGIN
+    g_debugImage = cr::decodeImageFile(path ? path : "");
+    *w = g_debugImage.width;
+    *h = g_debugImage.height;
+    return true;
+    CR_GUARD_END(false)
+}
+void crDebugCopyDecodedImage(unsigned char* outRgba)
+{ if (!g_debugImage.pixels.empty()) memcpy(outRgba, g_debugImage.pixels.data(), g_debugImage.pixels.size()); }
 int crDebugGetMissShader(void) { return renderer().scene().missShader; }
 size_t crDebugGetTextureCount(void) { return renderer().scene().textures.size(); }
 void crDebugGetTextureSize(int index, int* w, int* h)

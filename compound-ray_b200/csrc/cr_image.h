@@ -3,7 +3,7 @@
 // image reaches MulticamScene::addImage (libEyeRenderer3/MulticamScene.cpp:753-798) as 4-channel
 // 8-bit RGBA, row 0 first.  Only the formats the shipped scenes use are implemented here:
 // non-interlaced PNG, bit depth 8 (grey, grey+alpha, RGB, RGBA, palette) and 16 (reduced to the
-// high byte).  JPEG is a "next" row and is rejected with an error.
+// high byte), and baseline JPEG (cr_jpeg.h).
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -147,10 +147,11 @@ inline ImageRGBA8 decodePNG(const uint8_t* data, size_t size)
     return res;
 }
 
+ImageRGBA8 decodeJPEG(const uint8_t* data, size_t size);   // cr_jpeg.h
+
 inline ImageRGBA8 decodeImage(const uint8_t* data, size_t size)
 {
-    if (size >= 2 && data[0] == 0xFF && data[1] == 0xD8)
-        throw std::runtime_error("JPEG textures are not supported yet (SURVEY.md 8f.3)");
+    if (size >= 2 && data[0] == 0xFF && data[1] == 0xD8) return decodeJPEG(data, size);
     return decodePNG(data, size);
 }
 

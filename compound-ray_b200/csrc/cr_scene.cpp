@@ -13,6 +13,7 @@
 #include <sstream>
 #include <stdexcept>
 
+#include "cr_jpeg.h"
 #include "cr_json.h"
 #include "cr_math.h"
 
@@ -454,6 +455,12 @@ std::vector<Ommatidium> readEyeFile(const std::string& path)
         out.push_back({v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]});
     }
     return out;
+}
+
+ImageRGBA8 decodeImageFile(const std::string& path)
+{
+    const std::vector<uint8_t> bytes = readFileBytes(path);
+    return decodeImage(bytes.data(), bytes.size());
 }
 
 HostScene loadGltfScene(const std::string& path, bool verbose)

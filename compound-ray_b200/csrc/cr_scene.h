@@ -85,6 +85,9 @@ struct HostScene {
 // Loads an ASCII .gltf (embedded base64 or external buffers/images).  Throws std::runtime_error.
 HostScene loadGltfScene(const std::string& path, bool verbose);
 
+// Decodes a PNG / baseline-JPEG file to RGBA8 (the texture path of the loader).
+ImageRGBA8 decodeImageFile(const std::string& path);
+
 // .eye parsing (MulticamScene.cpp:290-299; data/eyes/eye-specification.txt)
 std::vector<Ommatidium> readEyeFile(const std::string& path);
 

@@ -109,6 +109,9 @@ def configureFunctions(eyeRenderer):
     r.crGetLastTraceMs.restype = C.c_double
     r.crGetLaunchCount.restype = C.c_ulonglong
     r.crGetBvhBuildMs.restype = C.c_double
+    r.crDebugDecodeImageFile.argtypes = [C.c_char_p, vp, vp]
+    r.crDebugDecodeImageFile.restype = C.c_bool
+    r.crDebugCopyDecodedImage.argtypes = [vp]
     r.crDebugGetTextureSize.argtypes = [C.c_int, vp, vp]
     r.crDebugCopyTexture.argtypes = [C.c_int, vp]
     for name in ("crDebugGetTriangleCount", "crDebugGetVertexCount", "crDebugGetMeshCount", "crDebugGetBvhNodeCount",

@@ -125,6 +125,8 @@ void crDebugCopyCameraPose(float* out12);        /* current camera: position, x,
 void crDebugCopyCameraScale(float* out3);
 int crDebugGetCameraKind(void);                  /* 0 perspective, 1 panoramic, 2 orthographic, 3 compound */
 void crDebugCopyOmmatidia(float* out8);
+bool crDebugDecodeImageFile(const char* path, int* w, int* h);  /* PNG / baseline JPEG through the loader's decoder */
+void crDebugCopyDecodedImage(unsigned char* outRgba);
 int crDebugGetMissShader(void);
 size_t crDebugGetTextureCount(void);
 void crDebugGetTextureSize(int index, int* w, int* h);

@@ -271,3 +271,59 @@ def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
     b = L.getGeometryMaxBounds(b"Cube")
     assert b.toNumpy().tolist() == [1.0, 1.0, 1.0]
     assert ref_helper.readEyeFile(os.path.join(ref_data, "data", "test-scene", "test100.eye"))[99].acceptanceAngle == 1.0
+
+
+def test_jpeg_decoder_matches_reference_stb_image(lib):
+    """Baseline JPEG textures decode to exactly the bytes the reference's vendored stb_image produces
+    (tests/golden/stb_jpeg_kat.npz, generated by oracle/kat/stb_kat.cpp compiled against
+    /root/reference/support/tinygltf/stb_image.h with req_comp = 4): 4:4:4, 4:2:2, 4:2:0, greyscale,
+    odd sizes, optimised Huffman tables.  Progressive streams are rejected loudly."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "stb_jpeg_kat.npz"))
+    jdir = os.path.join(ROOT, "tests", "golden", "jpeg")
+    names = sorted(f for f in os.listdir(jdir) if f.endswith(".jpg"))
+    assert len(names) >= 10
+    for name in names:
+        w, h = C.c_int(), C.c_int()
+        ok = lib.crDebugDecodeImageFile(os.path.join(jdir, name).encode(), C.byref(w), C.byref(h))
+        if "progressive" in name:
+            assert not ok
+            continue
+        assert ok, name
+        px = np.zeros((h.value, w.value, 4), np.uint8)
+        lib.crDebugCopyDecodedImage(px.ctypes.data)
+        assert np.array_equal(px, gold[name]), name
+
+
+def test_scene_with_external_jpeg_texture(lib, tmp_path):
+    """glTF with an external-file JPEG image (the ofstad arena's texture form) loads through the same path."""
+    import base64
+    import shutil
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "jpeg", "tex_420_128x96.jpg"), tmp_path / "pattern.jpg")
+    v = np.array([[-1, 0, -1], [1, 0, -1], [1, 0, 1], [-1, 0, 1]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    blob = v.tobytes() + uv.tobytes() + idx.tobytes()
+    gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0, "name": "floor"}],
+            "meshes": [{"name": "floor", "primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}]}],
+            "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+            "textures": [{"source": 0}], "images": [{"uri": "pattern.jpg"}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3", "min": [-1, 0, -1], "max": [1, 0, 1]},
+                          {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                          {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 48}, {"buffer": 0, "byteOffset": 48, "byteLength": 32},
+                            {"buffer": 0, "byteOffset": 80, "byteLength": 12}],
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    p = tmp_path / "jpeg_scene.gltf"
+    p.write_text(json.dumps(gltf))
+    lib.loadGlTFscene(str(p).encode())
+    assert lib.crDebugGetTriangleCount() == 2 and lib.crDebugGetTextureCount() == 1
+    w, h = C.c_int(), C.c_int()
+    lib.crDebugGetTextureSize(0, C.byref(w), C.byref(h))
+    assert (w.value, h.value) == (128, 96)
+    px = np.zeros((96, 128, 4), np.uint8)
+    lib.crDebugCopyTexture(0, px.ctypes.data)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "stb_jpeg_kat.npz"))
+    assert np.array_equal(px, gold["tex_420_128x96.jpg"])
+    info = np.zeros((1, 4), np.int32)
+    lib.crDebugCopyMeshInfo(info.ctypes.data, None)
+    assert info[0, 1] == 1 and info[0, 2] == 0                       # has UVs, texture 0
