@@ -178,3 +178,37 @@ def test_batched_iterators_match_the_reference_loop(lib, er, ref_data):
     assert tuple(seen[8][2]) == (0, 0, 0) and seen[0][0].shape == (1, len(cfg))
     gap = 10 / 3
     assert np.allclose(seen[3][1].numpy(), np.array([1, 1, 0]) * gap - gap)
+
+
+def test_primary_example_call_sequence(lib, er, ref_data, tmp_path):
+    """The call sequence of python-examples/primary-example.py:20-98: every camera of the
+    test scene is rendered, 'displayed', saved as PPM and read back; compound eyes again at S=100."""
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    W = H = 200
+    er.setRenderSize(lib, W, H)
+    n = lib.getCameraCount()
+    assert n == 6
+    for i in range(n):
+        lib.renderFrame()
+        lib.displayFrame()                                               # headless no-op
+        ppm = tmp_path / f"cam{i}.ppm"
+        lib.saveFrameAs(str(ppm).encode())
+        frame = np.copy(lib.getFramePointer())
+        assert frame.shape == (H, W, 4)
+        raw = ppm.read_bytes()
+        assert raw.startswith(b"P6\n200 200\n255\n")
+        rgb = np.frombuffer(raw[len(b"P6\n200 200\n255\n"):], np.uint8).reshape(H, W, 3)
+        assert np.array_equal(rgb, frame[::-1, :, :3])                   # PPM is top-down, the frame bottom-up
+        assert frame[:, :, :3].std() > 1                                 # something was drawn
+        if lib.isCompoundEyeActive():
+            lib.setCurrentEyeSamplesPerOmmatidium(100)
+            lib.renderFrame()
+            lib.saveFrameAs(str(tmp_path / f"cam{i}_100.ppm").encode())
+            smooth = np.copy(lib.getFramePointer())
+            assert smooth.shape == (H, W, 4) and (smooth[:, :, 3] == 255).all()
+        lib.nextCamera()
+    assert lib.getCurrentCameraIndex() == 0
+    lib.stop()
+    assert lib.getCameraCount() == 0
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())   # usable again after stop()
+    assert lib.getCameraCount() == 6 and lib.renderFrame() > 0
