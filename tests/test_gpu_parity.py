@@ -402,3 +402,52 @@ def test_texture_unit_vs_oracle_emulation(lib, oracle, loader, ref_data):
     d = np.abs(got[:, :3] - want)
     assert d.max() < 1e-3 and d.mean() < 2e-5, (d.max(), d.mean())
     assert (got[:, 3] == 1.0).all()
+
+
+def test_coincident_and_degenerate_triangles(lib, er, loader, oracle, tmp_path):
+    """Tie policy and builder robustness: 40 copies of one triangle (identical Morton codes, equal t on
+    every hit -> the LOWEST primitive index must win regardless of traversal order), zero-area
+    triangles (never hit), and two coplanar overlapping triangles."""
+    import base64
+    import json
+    from tools import synth
+    tri = np.array([[-2, -1.5, 3], [2, -1.5, 3], [0, 2.5, 3]], np.float32)
+    v = [tri] * 40
+    v += [np.array([[0, 0, 2], [0, 0, 2], [1, 1, 2]], np.float32)] * 3            # zero area, in front of the stack
+    v += [np.array([[-3, -3, 5], [3, -3, 5], [0, 3, 5]], np.float32), np.array([[-3, -3, 5], [0, 3, 5], [3, -3, 5]], np.float32)]
+    v = np.concatenate(v).astype(np.float32)
+    blob = v.tobytes()
+    gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0, 1]}],
+            "nodes": [{"camera": 0, "name": "cam"}, {"mesh": 0, "name": "stack"}],
+            "cameras": [{"name": "cam", "type": "perspective", "perspective": {"yfov": 0.5, "znear": 0.1},
+                         "extras": {"compound-eye": "TRUE", "compound-projection": "single_dimension_fast", "compound-structure": "e.eye"}}],
+            "meshes": [{"name": "stack", "primitives": [{"attributes": {"POSITION": 0}}]}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": len(v), "type": "VEC3", "min": v.min(0).tolist(), "max": v.max(0).tolist()}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": len(blob)}],
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    path = str(tmp_path / "dups.gltf")
+    with open(path, "w") as f:
+        json.dump(gltf, f)
+    omm = synth.fibonacci_eye(200, radius=0.01, acceptance=0.4)
+    omm[:, 3:6] = omm[:, 3:6] * 0.3 + np.array([0, 0, 1], np.float32)             # mostly towards +z (glTF camera looks down -z: z axis flips)
+    omm[:, 3:6] /= np.linalg.norm(omm[:, 3:6], axis=1, keepdims=True)
+    synth.write_eye(str(tmp_path / "e.eye"), omm)
+    lib.loadGlTFscene(path.encode())
+    assert lib.crDebugGetTriangleCount() == 45 and lib.gotoCameraByName(b"cam")
+    lib.setCameraLocalSpace(1, 0, 0, 0, 1, 0, 0, 0, 1)                            # look along +z
+    N, S = 200, 8
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    sc, sh, ocam = load_oracle_scene(loader, oracle, path, "cam")
+    eye = oracle.CompoundEyeOracle(sh, ocam.ommatidia, oracle.make_pose(ocam.position), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    lib.crDebugSetRayDump(True)
+    lib.renderFrame(); eye.render_frame(method="brute")
+    o, d, h = _product_rays(lib, N * S)
+    lib.crDebugSetRayDump(False)
+    assert np.array_equal(h["prim"], eye.last["hits"]["prim"])
+    hit = h["prim"] >= 0
+    assert hit.sum() > 200
+    assert set(np.unique(h["prim"][hit]).tolist()) <= {0, 43, 44}, "coincident copies resolve to primitive 0; degenerate ones never hit"
+    assert (h["prim"][hit] == 0).sum() > 100
+    assert np.array_equal(_frame(er, lib, N, 1), eye.frame)
