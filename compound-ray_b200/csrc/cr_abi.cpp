@@ -298,6 +298,11 @@ void crDebugCopyBvh(float* nodes16, float* tris12)
     CR_GUARD_END()
 }
 void crDebugSetRayDump(bool on) { renderer().dumpRays = on; }
+void crDebugSetEntryFrontier(int on, int minSamples)
+{
+    renderer().entryFrontier = on;
+    if (minSamples >= 0) renderer().entryMinSamples = minSamples;
+}
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4)
 {
     CR_GUARD_BEGIN

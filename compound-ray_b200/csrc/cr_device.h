@@ -18,7 +18,9 @@
 //   meshes  MeshRec[nMeshes]
 // Compound eye (per camera):
 //   omm     float4[2*N]        the 32-byte ommatidium rows as loaded
-//   pre     float4[3*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp)
+//   pre     float4[3*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp, cone bound)
+//   entries int4[F*N]          per (frame, ommatidium): up to 4 BVH subtree roots its sample cone can reach
+//                              (near to far, packed from .x, 0x80000000 = none)
 //   rng     uint4[2*N*S]       32 B compact XORWOW state per sample stream, laid out [o][s]
 //             r[0] = (d, v0, v1, v2)   r[1] = (v3, v4, boxmuller_flag, boxmuller_extra bits)
 //   samples float[3*N*S]       per-sample colour/S, laid out [o][s] (12 B per ray, written by K1)
@@ -71,6 +73,7 @@ struct EyeParams {
     int S = 0;
     int nFrames = 1;              // frames (poses) covered by one launch
     const DevicePose* poses = nullptr;   // device array [nFrames]; nullptr: use `pose`
+    const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
     DevicePose pose;
 };
 
@@ -100,6 +103,7 @@ enum Projection : int {
 // kernel launchers (cr_kernels.cu)
 void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cudaStream_t stream);
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream);
+void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream);
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);
 void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);

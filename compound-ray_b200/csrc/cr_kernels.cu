@@ -124,6 +124,10 @@ __global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long l
 // Ommatidial sample ray (shaders.cu:648-662 generateOffsetRay/rotatePoint, :676-709)
 // ------------------------------------------------------------------------------------------
 #define CR_FWHM_SD_RATIO 2.35482004503094938202313865291f   /* shaders.cu:53 */
+#ifndef CR_CONE_SIGMAS
+#define CR_CONE_SIGMAS 4.0f
+#endif
+constexpr float kConeSigmas = CR_CONE_SIGMAS;   // sample rays with |splay| <= kConeSigmas*sd start from the entry frontier
 
 __device__ __forceinline__ V3 rotatePoint(V3 p, float angle, V3 axis)   // axis NOT re-normalised
 {
@@ -140,7 +144,7 @@ struct Ray { V3 o, d; float tmin; };
 // (identical operations in identical order, so the rays are bit-identical to evaluating
 // shaders.cu:652-709 per sample):
 //   pre[0] = (relPos - normalize(axis)*focal, sd = acceptance / FWHM_SD_RATIO)
-//   pre[1] = (axis, focal)          pre[2] = (perp, 0)
+//   pre[1] = (axis, focal)          pre[2] = (perp, kConeSigmas*|sd| = splay bound of the entry cone)
 __global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* __restrict__ pre)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,15 +160,17 @@ __global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* _
     const V3 rp = vsub(relPos, vmuls(vnormalize(axis), focal));
     pre[3 * o + 0] = make_float4(rp.x, rp.y, rp.z, sd);
     pre[3 * o + 1] = make_float4(axis.x, axis.y, axis.z, focal);
-    pre[3 * o + 2] = make_float4(perp.x, perp.y, perp.z, 0.0f);
+    pre[3 * o + 2] = make_float4(perp.x, perp.y, perp.z, kConeSigmas * fabsf(sd));
 }
 
-__device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const DevicePose& P, Rng& rng)
+__device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const DevicePose& P, Rng& rng,
+                                             float& splayOut)
 {
     const V3 rp = mk(p0.x, p0.y, p0.z);
     const V3 axis = mk(p1.x, p1.y, p1.z);
     const V3 perp = mk(p2.x, p2.y, p2.z);
     const float splay = rngNormal(rng) * p0.w;
+    splayOut = splay;
     const float axisAngle = rngUniform(rng) * crm::kPi;
     const V3 splayed = rotatePoint(axis, splay, perp);
     const V3 rd = rotatePoint(splayed, axisAngle, axis);
@@ -287,7 +293,8 @@ struct Stack {
 template <bool COUNT>
 __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll, size_t variantStride,
                                             const float4* __restrict__ tris, const Ray& ray, const float tmax, int* sStackLane,
-                                            int stackStride, int* nodeCount, int* triCount)
+                                            int stackStride, int* nodeCount, int* triCount,
+                                            const int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel))
 {
     RayBox rb;
     int sx, sy, sz;
@@ -300,7 +307,15 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
     best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
     Stack st;
     st.smem = sStackLane; st.stride = stackStride; st.sp = 0;
-    int cur = 0;
+    // Entry refs (k_buildEntries) are packed from .x and sorted near to far; the default is the root.
+    int cur = entry.x;
+    if (entry.y != kSentinel) {
+        if (entry.z != kSentinel) {
+            if (entry.w != kSentinel) st.push(entry.w);
+            st.push(entry.z);
+        }
+        st.push(entry.y);
+    }
     int nc = 0, tc = 0;
     for (;;) {
         while (cur >= 0) {
@@ -398,6 +413,154 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 }
 
 // ------------------------------------------------------------------------------------------
+// K0b.  Entry frontier.  All sample rays of one ommatidium leave ONE origin inside a narrow cone
+// around its axis (angle to the axis <= |splay|: a rotation by splay moves a vector by at most
+// splay, the second rotation is about the axis itself).  Instead of walking the top of the BVH once
+// per sample, one thread per (frame, ommatidium) walks it once per frame with a conservative
+// cone/box test and leaves up to kEntryK subtree roots; the samples start there.  The closest
+// hit is unchanged: a subtree is dropped only when its box lies wholly outside one face of a
+// square pyramid circumscribing the cone widened by 1 % + 1 mrad (orders of magnitude above the
+// rounding of either test), so no ray of the cone could have passed the slab test of that box.
+// Rays drawn outside kConeSigmas, eyes whose axes are not unit length, poses that are not
+// orthonormal (then the bound above does not hold) and cones wider than 1 rad start at the root.
+// ------------------------------------------------------------------------------------------
+constexpr int kEntryK = 4;
+
+struct ConePyramid { V3 apex, axis, n0, n1, n2, n3; };
+
+__device__ __forceinline__ bool coneMayTouchBox(const ConePyramid& P, const V3 bmin, const V3 bmax)
+{
+    const V3 lo = vsub(bmin, P.apex), hi = vsub(bmax, P.apex);
+    const float scale = fmaxf(fmaxf(fmaxf(fabsf(P.apex.x), fabsf(P.apex.y)), fabsf(P.apex.z)),
+                              fmaxf(fmaxf(fmaxf(fabsf(bmin.x), fabsf(bmin.y)), fmaxf(fabsf(bmin.z), fabsf(bmax.x))),
+                                    fmaxf(fabsf(bmax.y), fabsf(bmax.z))));
+    const float tol = scale * 1.52587890625e-05f;      // 2^-16 of the coordinate magnitude >> rounding of lo/hi
+    const V3 n[4] = {P.n0, P.n1, P.n2, P.n3};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                       // least signed distance of the box to face i
+        const float m = fminf(n[i].x * lo.x, n[i].x * hi.x) + fminf(n[i].y * lo.y, n[i].y * hi.y) + fminf(n[i].z * lo.z, n[i].z * hi.z);
+        if (m > tol) return false;                      // (NaN compares false: never culls)
+    }
+    const float M = fmaxf(P.axis.x * lo.x, P.axis.x * hi.x) + fmaxf(P.axis.y * lo.y, P.axis.y * hi.y) + fmaxf(P.axis.z * lo.z, P.axis.z * hi.z);
+    if (M < -tol) return false;                         // wholly behind the apex
+    return true;
+}
+
+// kEntryK lanes work on one (frame, ommatidium): lane j owns slot j of the frontier, fetches that
+// node and tests its two child boxes; the four results are exchanged by shuffles and every lane
+// applies the same replacement rules to its replica of the list.  The descent is a chain of
+// dependent node fetches, so the slots advancing together cut its length from (entries x depth)
+// to about the depth.
+struct EntryList {
+    int ref[kEntryK];
+    float key[kEntryK];
+    unsigned fin;      // bit j: slot j is final (a leaf child, or no room to split)
+    int n;
+};
+__device__ __forceinline__ void entryAppend(EntryList& L, int ref, float key, bool fin)
+{
+#pragma unroll
+    for (int k = 0; k < kEntryK; k++)
+        if (k == L.n) { L.ref[k] = ref; L.key[k] = key; }
+    if (fin) L.fin |= 1u << L.n;
+    L.n++;
+}
+
+__global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, const EyeParams ep, int4* __restrict__ entries)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = tid / kEntryK;
+    const int lane = (int)(tid % kEntryK);
+    const int F = ep.poses ? ep.nFrames : 1;
+    const bool live = idx < (long long)ep.N * F;
+    const int f = live ? (int)(idx / ep.N) : 0, o = live ? (int)(idx - (long long)f * ep.N) : 0;
+    DevicePose P = ep.pose;
+    if (ep.poses) P = ep.poses[f];
+    const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
+    const V3 rp = mk(p0.x, p0.y, p0.z), a = mk(p1.x, p1.y, p1.z);
+    const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
+    const float half = p2.w * 1.01f + 1.0e-3f;
+    const float tolU = 1.0e-4f;
+    bool ok = live && half <= 1.0f;
+    ok = ok && fabsf(vdot(a, a) - 1.0f) <= tolU;
+    ok = ok && fabsf(vdot(X, X) - 1.0f) <= tolU && fabsf(vdot(Y, Y) - 1.0f) <= tolU && fabsf(vdot(Z, Z) - 1.0f) <= tolU;
+    ok = ok && fabsf(vdot(X, Y)) <= tolU && fabsf(vdot(X, Z)) <= tolU && fabsf(vdot(Y, Z)) <= tolU;
+    ConePyramid C;
+    C.apex = vadd(vadd(vadd(mk(P.px, P.py, P.pz), vmuls(X, rp.x)), vmuls(Y, rp.y)), vmuls(Z, rp.z));   // = Ray::o of every sample
+    C.axis = vnormalize(vadd(vadd(vmuls(X, a.x), vmuls(Y, a.y)), vmuls(Z, a.z)));
+    const V3 t = fabsf(C.axis.x) < 0.57f ? mk(1.0f, 0.0f, 0.0f) : (fabsf(C.axis.y) < 0.57f ? mk(0.0f, 1.0f, 0.0f) : mk(0.0f, 0.0f, 1.0f));
+    const V3 u = vnormalize(vcross(C.axis, t));
+    const V3 v = vcross(C.axis, u);
+    float sh, ch;
+    crm::sincos(half, sh, ch);
+    const V3 back = vmuls(C.axis, -sh);
+    C.n0 = vadd(vmuls(u, ch), back);
+    C.n1 = vadd(vmuls(u, -ch), back);
+    C.n2 = vadd(vmuls(v, ch), back);
+    C.n3 = vadd(vmuls(v, -ch), back);
+
+    EntryList L;
+#pragma unroll
+    for (int k = 0; k < kEntryK; k++) { L.ref[k] = kSentinel; L.key[k] = 0.0f; }
+    L.ref[0] = 0;
+    L.n = 1;
+    L.fin = ok ? 0u : 1u;                       // not ok: the root stays the only entry
+    for (int iter = 0; iter < 256; iter++) {
+        int myRef = kSentinel;
+#pragma unroll
+        for (int k = 0; k < kEntryK; k++) if (k == lane) myRef = L.ref[k];
+        const bool active = lane < L.n && !((L.fin >> lane) & 1u);
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;       // warp-uniform exit
+        int r0 = kSentinel, r1 = kSentinel, flags = 0;
+        float k0 = 0.0f, k1 = 0.0f;
+        if (active) {
+            const float4* np = sc.nodes + 4 * (size_t)myRef;        // octant variant 0 = (min, max)
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            const V3 min0 = mk(n0.x, n0.z, n2.x), max0 = mk(n0.y, n0.w, n2.y);
+            const V3 min1 = mk(n1.x, n1.z, n2.z), max1 = mk(n1.y, n1.w, n2.w);
+            const bool h0 = coneMayTouchBox(C, min0, max0), h1 = coneMayTouchBox(C, min1, max1);
+            r0 = __float_as_int(n3.x); r1 = __float_as_int(n3.y);
+            k0 = vdot(C.axis, vsub(vmuls(vadd(min0, max0), 0.5f), C.apex));
+            k1 = vdot(C.axis, vsub(vmuls(vadd(min1, max1), 0.5f), C.apex));
+            // never hand out leaves: their triangles would be tested without the per-ray box test
+            const bool stop = (h0 && r0 < 0) || (h1 && r1 < 0);
+            flags = 1 | (h0 ? 2 : 0) | (h1 ? 4 : 0) | (stop ? 8 : 0);
+        }
+        EntryList Nw;
+#pragma unroll
+        for (int k = 0; k < kEntryK; k++) { Nw.ref[k] = kSentinel; Nw.key[k] = 0.0f; }
+        Nw.n = 0; Nw.fin = 0u;
+        const int nOld = L.n;
+#pragma unroll
+        for (int i = 0; i < kEntryK; i++) {
+            const int fl = __shfl_sync(0xffffffffu, flags, i, kEntryK);
+            const int c0 = __shfl_sync(0xffffffffu, r0, i, kEntryK), c1 = __shfl_sync(0xffffffffu, r1, i, kEntryK);
+            const float q0 = __shfl_sync(0xffffffffu, k0, i, kEntryK), q1 = __shfl_sync(0xffffffffu, k1, i, kEntryK);
+            if (i < nOld) {
+                const int cnt = ((fl >> 1) & 1) + ((fl >> 2) & 1);
+                const bool wasFin = (L.fin >> i) & 1u;
+                if (!(fl & 1)) entryAppend(Nw, L.ref[i], L.key[i], wasFin);
+                else if ((fl & 8) || Nw.n + cnt + (nOld - 1 - i) > kEntryK) entryAppend(Nw, L.ref[i], L.key[i], true);
+                else {
+                    if (fl & 2) entryAppend(Nw, c0, q0, false);
+                    if (fl & 4) entryAppend(Nw, c1, q1, false);
+                }
+            }
+        }
+        L = Nw;
+    }
+    if (!live || lane != 0) return;
+    // near to far along the axis (kEntryK = 4: fixed compare-exchange network, empty slots last)
+#pragma unroll
+    for (int k = 0; k < kEntryK; k++) if (k >= L.n) L.key[k] = 3.0e38f;
+    auto cswap = [&](int x, int y) {
+        if (L.key[x] > L.key[y]) { const float tk = L.key[x]; L.key[x] = L.key[y]; L.key[y] = tk; const int tr = L.ref[x]; L.ref[x] = L.ref[y]; L.ref[y] = tr; }
+    };
+    cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+    entries[idx] = make_int4(L.ref[0], L.ref[1], L.ref[2], L.ref[3]);
+}
+
+// ------------------------------------------------------------------------------------------
 // K1.  Persistent warps; work unit = 32 consecutive sample rays r = o*S + s (lanes hold
 // consecutive samples of one ommatidium -> coherent rays, one coalesced 1 KB RNG-state read and
 // one coalesced 384 B colour write per warp).  No block-level synchronisation: per-sample
@@ -432,7 +595,10 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 pose.yz = c.x; pose.zx = c.y; pose.zy = c.z; pose.zz = c.w;
             }
             const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
-            const Ray ray = ommatidialRay(p0, p1, p2, pose, rng);
+            float splay;
+            const Ray ray = ommatidialRay(p0, p1, p2, pose, rng, splay);
+            int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
+            if (ep.entries != nullptr && fabsf(splay) <= p2.w) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
             if (MULTI) {   // park the state in shared memory: its 8 registers are dead while the ray is traced
                 sRng[0][threadIdx.x] = make_uint4(rng.d, rng.v0, rng.v1, rng.v2);
                 sRng[1][threadIdx.x] = make_uint4(rng.v3, rng.v4, (uint32_t)rng.flag, __float_as_uint(rng.extra));
@@ -440,7 +606,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 rngStore(statePtr, rng);
             }
             const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x],
-                                              kTraceThreads, nullptr, nullptr);
+                                              kTraceThreads, nullptr, nullptr, entry);
             const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
             float* dst = ep.samples + 3 * ((size_t)f * total + r);
             __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
@@ -706,6 +872,13 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     const long long nf = (long long)eye.N * eye.nFrames;
     k_sumSamples<<<(unsigned)((3 * nf + 127) / 128), 128, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed);
+}
+
+void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream)
+{
+    const long long total = (long long)eye.N * (eye.poses ? eye.nFrames : 1) * kEntryK;
+    if (total <= 0) return;
+    k_buildEntries<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(sc, eye, entries);
 }
 
 int traceKernelOccupancy()

@@ -55,7 +55,11 @@ Renderer& renderer()
     return r;
 }
 
-Renderer::Renderer() {}
+Renderer::Renderer()
+{
+    if (const char* e = getenv("CR_ENTRY_FRONTIER")) entryFrontier = atoi(e);
+    if (const char* e = getenv("CR_ENTRY_MIN_S")) entryMinSamples = atoi(e);
+}
 Renderer::~Renderer()
 {
     // process teardown: the CUDA context may already be gone; do not touch the device here
@@ -108,7 +112,8 @@ void Renderer::freeCompound(CompoundState& cs)
 {
     dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
-    dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses);
+    dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries);
+    cs.entryCap = 0;
     cs.batchSampleCap = cs.batchSummedCap = cs.batchPoseCap = 0;
     cs.dumpCap = 0;
     cs.rngN = cs.rngS = 0;
@@ -356,6 +361,22 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
     }
 }
 
+// Entry frontier of this launch's (frame, ommatidium) cones; leaves ep.entries null when switched off
+// or when there are too few samples per ommatidium to amortise the pass.
+void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
+{
+    if (!entryFrontier || cs.S < entryMinSamples || cs.N <= 0) return;
+    const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(ep.poses ? ep.nFrames : 1);
+    if (cs.entryCap < need) {
+        dfree(cs.dEntries);
+        cs.dEntries = dallocT<int4>(need);
+        cs.entryCap = need;
+    }
+    launchBuildEntries(dscene_, ep, cs.dEntries, stream_);
+    launches_++;
+    ep.entries = cs.dEntries;
+}
+
 void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose)
 {
     EyeParams ep;
@@ -377,6 +398,7 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
         }
         ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH;
     }
+    buildEntries(cs, ep);
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;   // persistent grid: every SM full
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;   // trace + ordered sum
@@ -394,6 +416,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     ep.S = cs.S;
     ep.nFrames = nFrames;
     ep.poses = dPoses;
+    buildEntries(cs, ep);
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;
@@ -569,6 +592,11 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         cs.dBatchSummed = dallocT<float4>(F * N);
         CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
         cs.batchSummedCap = F * N;
+    }
+    if (entryFrontier && cs.S >= entryMinSamples && cs.entryCap < F * N) {   // keep the allocation out of the timed region
+        dfree(cs.dEntries);
+        cs.dEntries = dallocT<int4>(F * N);
+        cs.entryCap = F * N;
     }
     if (cs.batchPoseCap < count) {
         dfree(cs.dBatchPoses);

@@ -35,6 +35,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     // multi-frame batch buffers (crRenderPoseBatch)
     float* dBatchSamples = nullptr; float4* dBatchSummed = nullptr; DevicePose* dBatchPoses = nullptr;
     size_t batchSampleCap = 0, batchSummedCap = 0, batchPoseCap = 0;
+    int4* dEntries = nullptr; size_t entryCap = 0;   // entry frontier [frames][N] (k_buildEntries)
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; size_t dumpCap = 0;
 };
@@ -67,6 +68,8 @@ public:
 
     bool verbose = true;
     bool dumpRays = false;
+    int entryFrontier = 1;             // 0: every sample ray starts at the BVH root (A/B switch, crDebugSetEntryFrontier)
+    int entryMinSamples = 8;           // below this S the per-frame frontier pass costs more than it saves
     int width() const { return W_; }
     int height() const { return H_; }
 
@@ -97,6 +100,7 @@ private:
     void prepareCompound(CompoundState& cs, HostCamera& cam);
     void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose);
     void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed);
+    void buildEntries(CompoundState& cs, EyeParams& ep);
     void project(CompoundState& cs, const HostCamera& cam);
     void ensureFrame();
     void freeCompound(CompoundState& cs);

@@ -64,6 +64,73 @@ def test_cfg4_million_triangle_terrain_10k_eye(lib, er, loader, oracle, terrain)
     assert np.array_equal(hits2["prim"], h["prim"]) and cnt[0] / (N * S) < 40
 
 
+def _stress_eye(n, seed):
+    """Ommatidia that exercise every branch of the entry-frontier pass: zero / narrow / wide / very wide
+    acceptance angles, focal offsets, positions off the eye centre, exactly vertical axes, axes that are
+    not unit length (frontier must fall back to the root) and the perp-sum==0 quirk (az == ax)."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    omm = np.zeros((n, 8), np.float32)
+    omm[:, 0:3] = d * 0.05 + rng.normal(scale=0.01, size=(n, 3))
+    omm[:, 3:6] = d
+    omm[:, 6] = np.radians(rng.choice([0.0, 0.05, 1.0, 2.3, 8.0, 20.0, 35.0, 60.0, 120.0], size=n))
+    omm[:, 7] = rng.choice([0.0, 0.0, 0.01, 0.5, -0.2], size=n)
+    omm[0, 3:6] = (0, 1, 0); omm[1, 3:6] = (0, -1, 0)
+    omm[2, 3:6] = (0.6, 0.52915026, 0.6)                 # az == ax: perp falls back to (0,0,1), not perpendicular
+    omm[3:40, 3:6] *= rng.uniform(0.5, 2.0, size=(37, 1)).astype(np.float32)   # non-unit axes
+    omm[40:60, 3:6] *= np.float32(1.00002)               # inside the unit-length tolerance
+    return omm
+
+
+def test_entry_frontier_equals_root_traversal(lib, er, terrain):
+    """The per-ommatidium entry frontier (k_buildEntries) only removes work: with it switched on and off,
+    the same RNG streams give bit-identical hits (prim, t, u, v), ommatidial RGB and batch rows, for a stress eye
+    at poses above, inside, beside and far from the terrain, axis-aligned and rotated."""
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    N, S = 2048, 32
+    omm = _stress_eye(N, 7)
+    er.setOmmatidiaFromArray(lib, omm)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    er.setRenderSize(lib, N, 1)
+    rng = np.random.default_rng(11)
+    poses = []
+    for pos in ([0, 12, 0], [3.3, 0.7, -41.0], [49.9, 2.0, 49.9], [0, -5, 0], [400, 50, 0], [0.001, 3.0, 0.001], [-20, 0.05, 7]):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        poses.append(np.concatenate([np.float32(pos), q[:, 0], q[:, 1], q[:, 2]]))
+        poses.append(np.concatenate([np.float32(pos), [1, 0, 0, 0, 1, 0, 0, 0, 1]]))
+    poses = np.asarray(poses, np.float32)
+    res = {}
+    for mode in (0, 1):
+        lib.crDebugSetEntryFrontier(mode, 8)
+        lib.setCurrentEyeSamplesPerOmmatidium(S)          # resets the streams: both modes draw the same rays
+        lib.crDebugSetRayDump(True)
+        per_pose = []
+        for p in poses:
+            lib.setCameraPosition(float(p[0]), float(p[1]), float(p[2]))
+            er.setCameraLocalSpace(lib, p[3:12].reshape(3, 3).T)
+            lib.renderFrame()
+            o = np.zeros((N * S, 3), np.float32); d = np.zeros((N * S, 3), np.float32); h = np.zeros(N * S, HIT4)
+            assert lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data) == N * S
+            per_pose.append((d.copy(), h.copy(), er.getOmmatidialData(lib).copy()))
+        lib.crDebugSetRayDump(False)
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
+        rows, _ = er.renderPoseBatch(lib, poses)
+        res[mode] = (per_pose, rows)
+    lib.crDebugSetEntryFrontier(1, 8)
+    n_hits = 0
+    for (d0, h0, c0), (d1, h1, c1) in zip(res[0][0], res[1][0]):
+        assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+        assert np.array_equal(h0["prim"], h1["prim"])
+        hit = h0["prim"] >= 0
+        n_hits += int(hit.sum())
+        for k in ("t", "u", "v"):
+            assert np.array_equal(h0[k][hit].view(np.uint32), h1[k][hit].view(np.uint32)), k
+        assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
+    assert n_hits > 100000
+    assert np.array_equal(res[0][1], res[1][1])
+
+
 def test_cfg4_full_sample_count_properties(lib, er, terrain):
     """S=1024 on the headline workload (10.24M rays/frame): the batch path, the per-frame ABI and a
     restarted (sharded) run produce byte-identical rows."""
