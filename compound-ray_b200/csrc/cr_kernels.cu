@@ -627,25 +627,62 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     }
 }
 
-// K1b: summed[f][o].ch = ((0 + c[f][o][0]) + c[f][o][1]) + ... + c[f][o][S-1], one thread per
-// (frame, ommatidium, channel): the reference's sequential fp32 order (shaders.cu:341-347).
-__global__ void k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed)
+// K1b: summed[f][o].ch = ((0 + c[f][o][0]) + c[f][o][1]) + ... + c[f][o][S-1]: the reference's sequential
+// fp32 order (shaders.cu:341-347), so each (row, channel) is one dependent chain of S additions.
+// A CTA owns kSumRows consecutive (frame, ommatidium) rows.  Its 96 threads stream tiles of
+// kSumChunk samples per row into shared memory with cp.async -- coalesced 384-byte pieces of the
+// 12*S contiguous bytes of a row ([row][s][3] layout), two tiles in flight, no registers held --
+// and the first 3*kSumRows threads (row, channel) walk their chains through the landed tile.
+// Row stride = 3 mod 32 floats: those 24 lanes hit 24 different banks.
+constexpr int kSumRows = 8, kSumChunk = 128, kSumThreads = 96, kSumStride = 3 * kSumChunk + 3, kSumStages = 3;
+
+__device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc)
 {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 3ll * NF) return;
-    const int o = (int)(k / 3), ch = (int)(k - 3ll * o);
-    const float* src = samples + 3 * (size_t)o * S + ch;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc));
+}
+
+__global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed)
+{
+    __shared__ float tile[kSumStages][kSumRows * kSumStride];
+    const int row0 = blockIdx.x * kSumRows;
+    const int rows = min(kSumRows, NF - row0);
+    const int t = threadIdx.x;
+    const size_t rowFloats = 3 * (size_t)S;
+    const float* base = samples + rowFloats * (size_t)row0;
+    const int nChunks = (S + kSumChunk - 1) / kSumChunk;
+    auto issue = [&](int c) {
+        if (c < nChunks) {
+            const int nf = 3 * min(kSumChunk, S - c * kSumChunk);
+            const float* src = base + 3 * (size_t)c * kSumChunk;
+            float* dst = tile[c % kSumStages];
+            for (int r = 0; r < rows; r++)
+#pragma unroll
+                for (int k = t; k < 3 * kSumChunk; k += kSumThreads)
+                    if (k < nf) cpAsync4(dst + r * kSumStride + k, src + rowFloats * r + k);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    issue(0);
+    issue(1);
+    const int myRow = t / 3, ch = t - 3 * myRow;
+    const bool summing = myRow < rows;               // threads 0 .. 3*rows-1, all in warp 0
     float sum = 0.0f;
-    int s = 0;
-    for (; s + 8 <= S; s += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = __ldg(src + 3 * (size_t)(s + j));
-#pragma unroll
-        for (int j = 0; j < 8; j++) sum += v[j];
+    for (int c = 0; c < nChunks; c++) {
+        asm volatile("cp.async.wait_group 1;");        // tile c has landed (tile c+1 may still be in flight)
+        __syncthreads();                                // ... for every thread; and everyone is done with tile c-1
+        issue(c + 2);                                   // reuses the stage of tile c-1
+        if (summing) {
+            const float* q = &tile[c % kSumStages][myRow * kSumStride + ch];
+            const int ns = min(kSumChunk, S - c * kSumChunk);
+            if (ns == kSumChunk) {
+#pragma unroll 16
+                for (int k = 0; k < kSumChunk; k++) sum += q[3 * k];
+            } else {
+                for (int k = 0; k < ns; k++) sum += q[3 * k];
+            }
+        }
     }
-    for (; s < S; s++) sum += __ldg(src + 3 * (size_t)s);
-    reinterpret_cast<float*>(summed + o)[ch] = sum;
+    if (summing) reinterpret_cast<float*>(summed + row0 + myRow)[ch] = sum;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -871,7 +908,7 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     else if (eye.poses) k_traceCompound<false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     const long long nf = (long long)eye.N * eye.nFrames;
-    k_sumSamples<<<(unsigned)((3 * nf + 127) / 128), 128, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed);
+    k_sumSamples<<<(unsigned)((nf + kSumRows - 1) / kSumRows), kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed);
 }
 
 void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream)

@@ -187,7 +187,7 @@ void Renderer::uploadScene()
     dIndices_ = dallocT<uint32_t>(3 * T);
     if (V) CR_CUDA(cudaMemcpyAsync(dPositions_, scene_.positions.data(), sizeof(float) * 3 * V, cudaMemcpyHostToDevice, stream_));
     if (T) CR_CUDA(cudaMemcpyAsync(dIndices_, scene_.indices.data(), sizeof(uint32_t) * 3 * T, cudaMemcpyHostToDevice, stream_));
-    int leafSize = 4;
+    int leafSize = 2;   // measured best with the entry frontier (1: 16.2, 2: 17.9, 4: 17.2, 8: 16.0 Grays/s)
     if (const char* env = getenv("CR_LEAF_SIZE")) leafSize = atoi(env);
     bvh_ = buildLbvh(dPositions_, dIndices_, static_cast<int>(T), smin, smax, leafSize, stream_);
     dfree(dPositions_);
