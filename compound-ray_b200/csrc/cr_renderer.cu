@@ -470,6 +470,7 @@ void Renderer::ensureFrame()
     frameCap_ = need;
     frameW_ = W_;
     frameH_ = H_;
+    hostFrameFresh_ = false;
 }
 
 void Renderer::setRenderSize(int w, int h)
@@ -501,6 +502,10 @@ double Renderer::renderFrame()
                      W_, H_, stream_);
         launches_++;
     }
+    // Small frames (eye vectors, thumbnails) ride back on the same stream, so the usual
+    // renderFrame -> getFramePointer pair costs one synchronisation instead of two.
+    hostFrameFresh_ = sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
+    if (hostFrameFresh_) CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
     CR_CUDA(cudaGetLastError());
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -518,8 +523,10 @@ unsigned char* Renderer::framePointer()
     if (verbose) std::cout << "[PyEye] Retrieving frame pointer..." << std::endl;
     ensureDevice();
     ensureFrame();
+    if (hostFrameFresh_) return hFrame_;              // already copied by renderFrame
     CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
+    hostFrameFresh_ = true;
     return hFrame_;
 }
 

@@ -134,6 +134,8 @@ private:
     uchar4* dFrame_ = nullptr;
     unsigned char* hFrame_ = nullptr;                             // pinned
     size_t frameCap_ = 0;
+    bool hostFrameFresh_ = false;                                 // hFrame_ already holds the last rendered frame
+    static constexpr size_t kEagerFrameBytes = size_t(1) << 20;
     int frameW_ = 0, frameH_ = 0;
 
     double lastTraceMs_ = 0.0;
