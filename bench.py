@@ -130,9 +130,11 @@ def poses_for(cam_pos, axes, count, first_index):
     return er.make_poses(pos, x=axes[0:3], y=axes[3:6], z=axes[6:9])
 
 
-def traversal_counters(lib, er, S_probe=8):
-    """n_node, n_tri per ray, counted by the CPU oracle's instrumented traversal of the IDENTICAL
-    device BVH on the product's own rays for this eye/pose (a probe frame at S_probe samples)."""
+def traversal_counters(lib, er, S_probe=32):
+    """Per-ray BVH nodes fetched / triangles tested, counted ON THE DEVICE by the dump variant of the trace
+    kernel (same code path, entry frontier included) on a probe frame of S_probe samples, plus the same
+    figures for a plain root-to-leaf traversal counted by the CPU oracle's instrumented walk of the IDENTICAL
+    device BVH on the product's own rays (which also re-checks the hit ids)."""
     from oracle import oracle as O
     N = lib.getCurrentEyeOmmatidialCount()
     S_keep = lib.getCurrentEyeSamplesPerOmmatidium()
@@ -142,6 +144,8 @@ def traversal_counters(lib, er, S_probe=8):
     n = N * S_probe
     o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); h = np.zeros((n, 4), np.int32)
     lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data)
+    cnt_dev = np.zeros((n, 2), np.int32)
+    assert lib.crDebugCopyLastRayCounts(cnt_dev.ctypes.data) == n
     lib.crDebugSetRayDump(False)
     T = lib.crDebugGetTriangleCount(); nn = lib.crDebugGetBvhNodeCount()
     nodes = np.zeros((nn, 16), np.float32); tris = np.zeros((T, 12), np.float32)
@@ -150,7 +154,8 @@ def traversal_counters(lib, er, S_probe=8):
     hits, cnt = O.trace_device_bvh(nodes, tris, o, d, tm)
     assert np.array_equal(hits["prim"], h[:, 0]), "oracle traversal of the device BVH disagrees with the kernel"
     lib.setCurrentEyeSamplesPerOmmatidium(S_keep)
-    return cnt[0] / n, cnt[1] / n, float((h[:, 0] >= 0).mean())
+    return {"nodes": float(cnt_dev[:, 0].mean()), "tris": float(cnt_dev[:, 1].mean()), "hit_fraction": float((h[:, 0] >= 0).mean()),
+            "nodes_from_root": cnt[0] / n, "tris_from_root": cnt[1] / n}
 
 
 def cpu_baseline(gltf, S, target_seconds=12.0, threads=None):
@@ -346,7 +351,8 @@ def main():
                "concurrently on its own GPU; max over ranks"}
 
         # -------------------------------------------------------------- roofline of the dominant kernel (K1)
-        n_node, n_tri, hit_frac = traversal_counters(lib, er)
+        tc = traversal_counters(lib, er)
+        n_node, n_tri, hit_frac = tc["nodes"], tc["tris"], tc["hit_fraction"]
         lib.crGetLastBatchFrames.restype = C.c_int
         F = max(1, int(frames_per_launch))
         # per ray: node + triangle fetches, RNG state read+write once per F-frame launch, 12 B sample write +
@@ -367,12 +373,14 @@ def main():
                     "dram_achieved_gbs": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
                     "kernel": "k_traceCompound<false,true>", "frames_per_launch": F,
                     "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_step * F, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                    "nodes_per_ray_from_root": tc["nodes_from_root"], "tris_per_ray_from_root": tc["tris_from_root"],
                     "hit_fraction": hit_frac, "peak_source": peak_src,
-                    "note": "achieved = SURVEY 8(d) algorithmic bytes (64*nodes + 48*tris + 64/F RNG r+w + 24 sample w+r + 48/S per ray) / time. The BVH "
-                            "bytes are L1/L2 hits (one viewpoint per frame), so frac exceeds 1: the kernel is NOT HBM-bound. "
+                    "note": "achieved = SURVEY 8(d) algorithmic bytes (64*nodes + 48*tris + 64/F RNG r+w + 24 sample w+r + 48/S per ray) / time, "
+                            "with nodes/tris per ray counted on the device by the dump variant of the kernel (entry frontier active; "
+                            "*_from_root = what a root-to-leaf walk of the same tree fetches; the per-ommatidium frontier pass adds < 0.1 B/ray). "
+                            "The BVH bytes are L1/L2 hits (one viewpoint per frame): the kernel is issue/latency-bound, not HBM-bound. "
                             "dram_* = ncu-measured DRAM bytes per launch (RNG state + samples) / live launch time: the true HBM "
-                            "utilisation. ncu: issue slots 65% busy, 23/32 lanes active, top stall long-scoreboard (node fetch "
-                            "latency) -- see profiles/r01_final_k1_ncu_summary.txt"}
+                            "utilisation -- see profiles/ for the ncu summaries"}
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(gltf, S)
         out = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

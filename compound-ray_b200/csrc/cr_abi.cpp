@@ -298,6 +298,12 @@ void crDebugCopyBvh(float* nodes16, float* tris12)
     CR_GUARD_END()
 }
 void crDebugSetRayDump(bool on) { renderer().dumpRays = on; }
+size_t crDebugCopyLastRayCounts(int32_t* counts2)
+{
+    CR_GUARD_BEGIN
+    return renderer().debugCopyLastRayCounts(counts2);
+    CR_GUARD_END(0)
+}
 void crDebugSetEntryFrontier(int on, int minSamples)
 {
     renderer().entryFrontier = on;

@@ -69,6 +69,7 @@ struct EyeParams {
     float* dumpOrigins = nullptr;
     float* dumpDirs = nullptr;
     int4* dumpHits = nullptr;     // (prim, t bits, u bits, v bits)
+    int2* dumpCounts = nullptr;   // (BVH nodes fetched, triangles tested) per sample ray
     int N = 0;
     int S = 0;
     int nFrames = 1;              // frames (poses) covered by one launch

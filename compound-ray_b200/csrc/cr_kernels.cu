@@ -605,8 +605,9 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
             } else {
                 rngStore(statePtr, rng);
             }
-            const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x],
-                                              kTraceThreads, nullptr, nullptr, entry);
+            int nNode = 0, nTri = 0;
+            const Hit h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x],
+                                             kTraceThreads, &nNode, &nTri, entry);
             const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
             float* dst = ep.samples + 3 * ((size_t)f * total + r);
             __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
@@ -621,6 +622,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
                 ep.dumpDirs[3 * id] = ray.d.x; ep.dumpDirs[3 * id + 1] = ray.d.y; ep.dumpDirs[3 * id + 2] = ray.d.z;
                 ep.dumpHits[id] = make_int4(h.prim, __float_as_int(h.t), __float_as_int(h.u), __float_as_int(h.v));
+                if (ep.dumpCounts) ep.dumpCounts[id] = make_int2(nNode, nTri);   // nodes fetched / triangles tested by THIS kernel
             }
         }
         if (MULTI) rngStore(statePtr, rng);

@@ -111,7 +111,7 @@ DevicePose Renderer::toDevicePose(const Pose& p)
 void Renderer::freeCompound(CompoundState& cs)
 {
     dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
-    dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
+    dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
     dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries);
     cs.entryCap = 0;
     cs.batchSampleCap = cs.batchSummedCap = cs.batchPoseCap = 0;
@@ -390,13 +390,14 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
     if (dumpRays) {
         const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
         if (cs.dumpCap < need) {
-            dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH);
+            dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
             cs.dDumpO = dallocT<float>(3 * need);
             cs.dDumpD = dallocT<float>(3 * need);
             cs.dDumpH = dallocT<int4>(need);
+            cs.dDumpC = dallocT<int2>(need);
             cs.dumpCap = need;
         }
-        ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH;
+        ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH; ep.dumpCounts = cs.dDumpC;
     }
     buildEntries(cs, ep);
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;   // persistent grid: every SM full
@@ -681,6 +682,16 @@ size_t Renderer::debugCopyLastRays(float* origins, float* dirs, int32_t* hits4)
     CR_CUDA(cudaMemcpy(origins, cs.dDumpO, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     CR_CUDA(cudaMemcpy(dirs, cs.dDumpD, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     CR_CUDA(cudaMemcpy(hits4, cs.dDumpH, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+size_t Renderer::debugCopyLastRayCounts(int32_t* counts2)
+{
+    if (!compoundActive()) return 0;
+    CompoundState& cs = compoundState(current_);
+    const size_t n = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
+    if (!cs.dDumpC || cs.dumpCap < n) return 0;
+    CR_CUDA(cudaMemcpy(counts2, cs.dDumpC, sizeof(int2) * n, cudaMemcpyDeviceToHost));
     return n;
 }
 

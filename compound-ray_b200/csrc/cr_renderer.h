@@ -37,7 +37,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     size_t batchSampleCap = 0, batchSummedCap = 0, batchPoseCap = 0;
     int4* dEntries = nullptr; size_t entryCap = 0;   // entry frontier [frames][N] (k_buildEntries)
     // debug dump buffers
-    float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; size_t dumpCap = 0;
+    float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; int2* dDumpC = nullptr; size_t dumpCap = 0;
 };
 
 class Renderer {
@@ -86,6 +86,7 @@ public:
     void debugCopyBvh(float* nodes, float* tris);
     int debugNodeCount() const { return bvh_.nNodes; }
     void debugCopyRngStates(uint32_t* out8);                      // [N*S][8] in reference stream-id order
+    size_t debugCopyLastRayCounts(int32_t* counts2);
     size_t debugCopyLastRays(float* origins, float* dirs, int32_t* hits4);
     void debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8);
     void debugCopyProjectionMap(uint32_t* out);

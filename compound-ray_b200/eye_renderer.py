@@ -127,6 +127,8 @@ def configureFunctions(eyeRenderer):
     r.crDebugCopyBvh.argtypes = [vp, vp]
     r.crDebugSetRayDump.argtypes = [C.c_bool]
     r.crDebugSetEntryFrontier.argtypes = [C.c_int, C.c_int]
+    r.crDebugCopyLastRayCounts.argtypes = [vp]
+    r.crDebugCopyLastRayCounts.restype = C.c_size_t
     r.crDebugCopyLastRays.argtypes = [vp, vp, vp]
     r.crDebugCopyLastRays.restype = C.c_size_t
     r.crDebugCopyRngStates.argtypes = [vp]

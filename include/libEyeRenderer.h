@@ -137,6 +137,7 @@ void crDebugSetRayDump(bool on);
 /* A/B switch of the per-ommatidium entry frontier (on by default for S >= 8); minSamples < 0 keeps the threshold. */
 void crDebugSetEntryFrontier(int on, int minSamples);
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* stream-id order N*s+o */
+size_t crDebugCopyLastRayCounts(int32_t* counts2); /* (BVH nodes fetched, triangles tested) per dumped ray, same order */
 void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */
 void crDebugTraceRays(const float* origins3, const float* dirs3, const float* tmins, int n, int32_t* hits8);
 void crDebugCopyProjectionMap(uint32_t* out);    /* W*H ommatidium indices of the cached map */

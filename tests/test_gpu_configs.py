@@ -112,14 +112,18 @@ def test_entry_frontier_equals_root_traversal(lib, er, terrain):
             lib.renderFrame()
             o = np.zeros((N * S, 3), np.float32); d = np.zeros((N * S, 3), np.float32); h = np.zeros(N * S, HIT4)
             assert lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data) == N * S
-            per_pose.append((d.copy(), h.copy(), er.getOmmatidialData(lib).copy()))
+            cnt = np.zeros((N * S, 2), np.int32)
+            assert lib.crDebugCopyLastRayCounts(cnt.ctypes.data) == N * S
+            per_pose.append((d.copy(), h.copy(), er.getOmmatidialData(lib).copy(), cnt.sum(axis=0)))
         lib.crDebugSetRayDump(False)
         lib.setCurrentEyeSamplesPerOmmatidium(S)
         rows, _ = er.renderPoseBatch(lib, poses)
         res[mode] = (per_pose, rows)
     lib.crDebugSetEntryFrontier(1, 8)
     n_hits = 0
-    for (d0, h0, c0), (d1, h1, c1) in zip(res[0][0], res[1][0]):
+    visits = np.zeros((2, 2), np.int64)
+    for (d0, h0, c0, n0), (d1, h1, c1, n1) in zip(res[0][0], res[1][0]):
+        visits[0] += n0; visits[1] += n1
         assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
         assert np.array_equal(h0["prim"], h1["prim"])
         hit = h0["prim"] >= 0
@@ -129,6 +133,7 @@ def test_entry_frontier_equals_root_traversal(lib, er, terrain):
         assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
     assert n_hits > 100000
     assert np.array_equal(res[0][1], res[1][1])
+    assert visits[1, 0] < visits[0, 0], "the frontier must only remove node fetches"
 
 
 def test_cfg4_full_sample_count_properties(lib, er, terrain):
