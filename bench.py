@@ -139,8 +139,10 @@ def traversal_counters(lib, er, S_probe=32):
     N = lib.getCurrentEyeOmmatidialCount()
     S_keep = lib.getCurrentEyeSamplesPerOmmatidium()
     lib.setCurrentEyeSamplesPerOmmatidium(S_probe)
+    lib.crDebugSetEntryFrontier(1, -1, 0)            # the probe frame is small: keep the frontier pass of the timed frames
     lib.crDebugSetRayDump(True)
     lib.renderFrame()
+    lib.crDebugSetEntryFrontier(1, -1, 3 << 18)
     n = N * S_probe
     o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); h = np.zeros((n, 4), np.int32)
     lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data)

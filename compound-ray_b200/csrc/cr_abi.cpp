@@ -304,10 +304,11 @@ size_t crDebugCopyLastRayCounts(int32_t* counts2)
     return renderer().debugCopyLastRayCounts(counts2);
     CR_GUARD_END(0)
 }
-void crDebugSetEntryFrontier(int on, int minSamples)
+void crDebugSetEntryFrontier(int on, int minSamples, long long minRays)
 {
     renderer().entryFrontier = on;
     if (minSamples >= 0) renderer().entryMinSamples = minSamples;
+    if (minRays >= 0) renderer().entryMinRays = minRays;
 }
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4)
 {

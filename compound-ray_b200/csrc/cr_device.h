@@ -74,6 +74,8 @@ struct EyeParams {
     int S = 0;
     int nFrames = 1;              // frames (poses) covered by one launch
     const DevicePose* poses = nullptr;   // device array [nFrames]; nullptr: use `pose`
+    uchar4* fastRow = nullptr;           // when set: K1b also writes make_color(summed[i]) for i < fastRowCount
+    int fastRowCount = 0;
     const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
     DevicePose pose;
 };
@@ -110,7 +112,6 @@ void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, i
 void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream);
 void launchProjectMap(bool ids, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream);
-void launchPackRow(const float4* summed, int N, uchar4* out, cudaStream_t stream);
 void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame,
                   int W, int H, cudaStream_t stream);
 void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,

@@ -643,7 +643,8 @@ __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc));
 }
 
-__global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed)
+__global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
+                                                            uchar4* __restrict__ fastRow, int fastRowCount)
 {
     __shared__ float tile[kSumStages][kSumRows * kSumStride];
     const int row0 = blockIdx.x * kSumRows;
@@ -685,6 +686,12 @@ __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restr
         }
     }
     if (summing) reinterpret_cast<float*>(summed + row0 + myRow)[ch] = sum;
+    // single_dimension_fast / pose-batch rows: pixel x IS ommatidium x (shaders.cu:389-406), so the 8-bit row is
+    // written here instead of by a separate projection launch.  Warp 0 holds (row, channel) at lane 3*row+ch.
+    if (fastRow != nullptr && t < 32) {
+        const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor(sum, g, b);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -713,14 +720,6 @@ __global__ void k_projectRaw(const float* __restrict__ samples, int N, int S, uc
     if (x >= W || y >= H || y >= S || x >= N) return;
     const float* p = samples + 3 * ((size_t)x * S + y);             // sample buffer is laid out [o][s]
     frame[(size_t)y * W + x] = makeColor(p[0], p[1], p[2]);
-}
-
-__global__ void k_packRow(const float4* __restrict__ summed, int N, uchar4* __restrict__ out)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= N) return;
-    const float4 c = __ldg(summed + x);
-    out[x] = makeColor(c.x, c.y, c.z);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -910,7 +909,8 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     else if (eye.poses) k_traceCompound<false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     const long long nf = (long long)eye.N * eye.nFrames;
-    k_sumSamples<<<(unsigned)((nf + kSumRows - 1) / kSumRows), kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed);
+    k_sumSamples<<<(unsigned)((nf + kSumRows - 1) / kSumRows), kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow,
+                                                                                         eye.fastRowCount);
 }
 
 void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream)
@@ -941,12 +941,6 @@ void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, 
     const int rows = H < S ? H : S;
     dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows);
     k_projectRaw<<<grid, 128, 0, stream>>>(samples, N, S, frame, W, H);
-}
-
-void launchPackRow(const float4* summed, int N, uchar4* out, cudaStream_t stream)
-{
-    if (N <= 0) return;
-    k_packRow<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(summed, N, out);
 }
 
 void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream)

@@ -59,6 +59,7 @@ Renderer::Renderer()
 {
     if (const char* e = getenv("CR_ENTRY_FRONTIER")) entryFrontier = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MIN_S")) entryMinSamples = atoi(e);
+    if (const char* e = getenv("CR_ENTRY_MIN_RAYS")) entryMinRays = atoll(e);
 }
 Renderer::~Renderer()
 {
@@ -363,9 +364,14 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
 
 // Entry frontier of this launch's (frame, ommatidium) cones; leaves ep.entries null when switched off
 // or when there are too few samples per ommatidium to amortise the pass.
+bool Renderer::entryFrontierActive(const CompoundState& cs, int frames) const
+{
+    return entryFrontier && cs.N > 0 && cs.S >= entryMinSamples && static_cast<long long>(cs.N) * cs.S * frames >= entryMinRays;
+}
+
 void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
 {
-    if (!entryFrontier || cs.S < entryMinSamples || cs.N <= 0) return;
+    if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1)) return;
     const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(ep.poses ? ep.nFrames : 1);
     if (cs.entryCap < need) {
         dfree(cs.dEntries);
@@ -377,9 +383,11 @@ void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
     ep.entries = cs.dEntries;
 }
 
-void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose)
+void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow, int fastRowCount)
 {
     EyeParams ep;
+    ep.fastRow = fastRow;
+    ep.fastRowCount = fastRowCount;
     ep.pre = cs.dPre;
     ep.rng = cs.dRng;
     ep.summed = cs.dSummed;
@@ -406,9 +414,12 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
     cs.frameIndex++;
 }
 
-void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed)
+void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
+                                   uchar4* fastRow)
 {
     EyeParams ep;
+    ep.fastRow = fastRow;
+    ep.fastRowCount = fastRow ? cs.N * nFrames : 0;
     ep.pre = cs.dPre;
     ep.rng = cs.dRng;
     ep.summed = dSummed;
@@ -494,18 +505,22 @@ double Renderer::renderFrame()
         CompoundState& cs = compoundState(current_);
         prepareCompound(cs, cam);
         CR_CUDA(cudaEventRecord(evA_, stream_));
-        launchCompound(cs, cam, cam.pose);
+        // single_dimension_fast: pixel x of row 0 is ommatidium x -- K1b writes the row itself
+        const bool fused = projectionFromName(cam.projection) == PROJ_SINGLE_DIM_FAST && W_ > 0 && H_ > 0;
+        launchCompound(cs, cam, cam.pose, fused ? dFrame_ : nullptr, fused ? std::min(cs.N, W_) : 0);
         CR_CUDA(cudaEventRecord(evB_, stream_));
         timedTrace = true;
-        project(cs, cam);
+        if (!fused) project(cs, cam);
     } else {
         launchCamera(dscene_, static_cast<int>(cam.kind), toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
                      W_, H_, stream_);
         launches_++;
     }
     // Small frames (eye vectors, thumbnails) ride back on the same stream, so the usual
-    // renderFrame -> getFramePointer pair costs one synchronisation instead of two.
-    hostFrameFresh_ = sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
+    // renderFrame -> getFramePointer pair costs one synchronisation instead of two.  Callers that
+    // did not read the previous frame (render-only timing loops) are not charged for the copy.
+    hostFrameFresh_ = frameWasFetched_ && sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
+    frameWasFetched_ = false;
     if (hostFrameFresh_) CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
     CR_CUDA(cudaGetLastError());
@@ -524,6 +539,7 @@ unsigned char* Renderer::framePointer()
     if (verbose) std::cout << "[PyEye] Retrieving frame pointer..." << std::endl;
     ensureDevice();
     ensureFrame();
+    frameWasFetched_ = true;
     if (hostFrameFresh_) return hFrame_;              // already copied by renderFrame
     CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
@@ -601,7 +617,7 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
         cs.batchSummedCap = F * N;
     }
-    if (entryFrontier && cs.S >= entryMinSamples && cs.entryCap < F * N) {   // keep the allocation out of the timed region
+    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.entryCap < F * N) {   // keep the allocation out of the timed region
         dfree(cs.dEntries);
         cs.dEntries = dallocT<int4>(F * N);
         cs.entryCap = F * N;
@@ -629,13 +645,10 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
             Pose pose;
             const float* q = poses12 + 12 * p0;
             pose.pos = {q[0], q[1], q[2]}; pose.ax = {q[3], q[4], q[5]}; pose.ay = {q[6], q[7], q[8]}; pose.az = {q[9], q[10], q[11]};
-            launchCompound(cs, cam, pose);
-            launchPackRow(cs.dSummed, cs.N, dOut + p0 * N, stream_);
+            launchCompound(cs, cam, pose, dOut + p0 * N, cs.N);
         } else {
-            launchCompoundBatch(cs, cs.dBatchPoses + p0, static_cast<int>(Fc), cs.dBatchSamples, cs.dBatchSummed);
-            launchPackRow(cs.dBatchSummed, static_cast<int>(Fc * N), dOut + p0 * N, stream_);
+            launchCompoundBatch(cs, cs.dBatchPoses + p0, static_cast<int>(Fc), cs.dBatchSamples, cs.dBatchSummed, dOut + p0 * N);
         }
-        launches_++;
     }
     CR_CUDA(cudaEventRecord(evB_, stream_));
     if (outRgba) CR_CUDA(cudaMemcpyAsync(outRgba, dOut, sizeof(uchar4) * N * count, cudaMemcpyDeviceToHost, stream_));

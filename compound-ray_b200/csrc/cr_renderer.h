@@ -69,7 +69,8 @@ public:
     bool verbose = true;
     bool dumpRays = false;
     int entryFrontier = 1;             // 0: every sample ray starts at the BVH root (A/B switch, crDebugSetEntryFrontier)
-    int entryMinSamples = 8;           // below this S the per-frame frontier pass costs more than it saves
+    int entryMinSamples = 8;           // below this S (or this many rays per launch) the frontier pass --
+    long long entryMinRays = 3ll << 18; // a chain of ~20 dependent node fetches, ~25 us -- costs more than it saves
     int width() const { return W_; }
     int height() const { return H_; }
 
@@ -99,8 +100,10 @@ private:
     void freeScene();
     CompoundState& compoundState(size_t camIdx);
     void prepareCompound(CompoundState& cs, HostCamera& cam);
-    void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose);
-    void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed);
+    void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow = nullptr, int fastRowCount = 0);
+    void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
+                             uchar4* fastRow = nullptr);
+    bool entryFrontierActive(const CompoundState& cs, int frames) const;   // frames = poses covered by the launch
     void buildEntries(CompoundState& cs, EyeParams& ep);
     void project(CompoundState& cs, const HostCamera& cam);
     void ensureFrame();
@@ -136,6 +139,7 @@ private:
     unsigned char* hFrame_ = nullptr;                             // pinned
     size_t frameCap_ = 0;
     bool hostFrameFresh_ = false;                                 // hFrame_ already holds the last rendered frame
+    bool frameWasFetched_ = true;                                 // the caller read the previous frame (getFramePointer/saveFrameAs)
     static constexpr size_t kEagerFrameBytes = size_t(1) << 20;
     int frameW_ = 0, frameH_ = 0;
 

@@ -126,7 +126,7 @@ def configureFunctions(eyeRenderer):
     r.crDebugCopyOmmatidia.argtypes = [vp]
     r.crDebugCopyBvh.argtypes = [vp, vp]
     r.crDebugSetRayDump.argtypes = [C.c_bool]
-    r.crDebugSetEntryFrontier.argtypes = [C.c_int, C.c_int]
+    r.crDebugSetEntryFrontier.argtypes = [C.c_int, C.c_int, C.c_longlong]
     r.crDebugCopyLastRayCounts.argtypes = [vp]
     r.crDebugCopyLastRayCounts.restype = C.c_size_t
     r.crDebugCopyLastRays.argtypes = [vp, vp, vp]

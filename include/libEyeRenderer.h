@@ -134,8 +134,9 @@ void crDebugCopyTexture(int index, unsigned char* outRgba);   /* decoded RGBA8, 
 size_t crDebugGetBvhNodeCount(void);
 void crDebugCopyBvh(float* nodes16, float* tris12);
 void crDebugSetRayDump(bool on);
-/* A/B switch of the per-ommatidium entry frontier (on by default for S >= 8); minSamples < 0 keeps the threshold. */
-void crDebugSetEntryFrontier(int on, int minSamples);
+/* A/B switch of the per-ommatidium entry frontier (default: on for S >= 8 and N*S >= 786432 rays per frame);
+ * negative thresholds keep the current value. */
+void crDebugSetEntryFrontier(int on, int minSamples, long long minRaysPerFrame);
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* stream-id order N*s+o */
 size_t crDebugCopyLastRayCounts(int32_t* counts2); /* (BVH nodes fetched, triangles tested) per dumped ray, same order */
 void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */

@@ -58,6 +58,9 @@ def lib(er):
     """The product library (loads without a GPU; rendering calls need one)."""
     L = er.load_library()
     L.setVerbosity(False)
+    # The parity tests use small frames; by default those skip the entry-frontier pass (it only pays above
+    # ~0.5M rays per frame).  Force it on for S >= 2 so every oracle comparison also exercises that path.
+    L.crDebugSetEntryFrontier(1, 2, 0)
     return L
 
 

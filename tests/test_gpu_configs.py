@@ -102,7 +102,7 @@ def test_entry_frontier_equals_root_traversal(lib, er, terrain):
     poses = np.asarray(poses, np.float32)
     res = {}
     for mode in (0, 1):
-        lib.crDebugSetEntryFrontier(mode, 8)
+        lib.crDebugSetEntryFrontier(mode, 8, 0)
         lib.setCurrentEyeSamplesPerOmmatidium(S)          # resets the streams: both modes draw the same rays
         lib.crDebugSetRayDump(True)
         per_pose = []
@@ -119,7 +119,7 @@ def test_entry_frontier_equals_root_traversal(lib, er, terrain):
         lib.setCurrentEyeSamplesPerOmmatidium(S)
         rows, _ = er.renderPoseBatch(lib, poses)
         res[mode] = (per_pose, rows)
-    lib.crDebugSetEntryFrontier(1, 8)
+    lib.crDebugSetEntryFrontier(1, 2, 0)
     n_hits = 0
     visits = np.zeros((2, 2), np.int64)
     for (d0, h0, c0, n0), (d1, h1, c1, n1) in zip(res[0][0], res[1][0]):
