@@ -204,6 +204,12 @@ void crSetFirstFrame(uint64_t frame)
     renderer().setFirstFrame(frame);
     CR_GUARD_END()
 }
+void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex)
+{
+    CR_GUARD_BEGIN
+    renderer().setOmmatidialShard(globalCount, firstIndex);
+    CR_GUARD_END()
+}
 double crGetLastTraceMs(void) { return renderer().lastTraceMs(); }
 unsigned long long crGetLaunchCount(void) { return renderer().launchCount(); }
 double crGetBvhBuildMs(void) { return renderer().bvhBuildMs(); }

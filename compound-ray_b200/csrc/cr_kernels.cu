@@ -103,12 +103,15 @@ __device__ __forceinline__ float rngNormal(Rng& r)
 // firstFrame > 0 positions the stream as if `firstFrame` frames had already been rendered
 // (pose sharding / restart): skipahead(2*floor(k/2)*... ) raw draws, plus one replayed frame when
 // k is odd so that the Box-Muller cache is populated exactly as in the sequential run.
-__global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long long firstFrame)
+// An ommatidium-range shard (crSetOmmatidialShard) holds rows [oFirst, oFirst+N) of an eye of nGlobal
+// ommatidia: the stream id keeps the GLOBAL indices, so a sharded frame equals the unsharded one.
+__global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal,
+                          unsigned long long oFirst)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)N * S) return;
     const int o = (int)(i / S), s = (int)(i - (long long)o * S);
-    const unsigned long long id = (unsigned long long)N * (unsigned long long)s + (unsigned long long)o;
+    const unsigned long long id = nGlobal * (unsigned long long)s + oFirst + (unsigned long long)o;
     curandStateXORWOW_t st;
     curand_init(42ull, id, 0ull, &st);
     const unsigned long long evenFrames = firstFrame & ~1ull;
@@ -885,12 +888,13 @@ __global__ void k_evalMath(int fn, const float* __restrict__ a, const float* __r
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, cudaStream_t stream)
+void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal, unsigned long long oFirst,
+                   cudaStream_t stream)
 {
     const long long n = (long long)N * S;
     if (n <= 0) return;
     const int tpb = 128;
-    k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame);
+    k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame, nGlobal, oFirst);
 }
 
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream)

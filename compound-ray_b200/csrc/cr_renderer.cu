@@ -322,6 +322,14 @@ void Renderer::setOmmatidia(const Ommatidium* omm, size_t count)
     cs.ommDirty = true;
     cs.eyeVersion++;
 }
+void Renderer::setOmmatidialShard(uint64_t globalCount, uint64_t first)
+{
+    if (!compoundActive()) return;
+    CompoundState& cs = compoundState(current_);
+    cs.shardGlobalN = globalCount;
+    cs.shardFirst = globalCount ? first : 0;
+    cs.randomsConfigured = false;
+}
 void Renderer::setFirstFrame(uint64_t k)
 {
     if (!compoundActive()) return;
@@ -355,7 +363,9 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
         cs.randomsConfigured = false;
     }
     if (!cs.randomsConfigured) {
-        launchRngInit(cs.dRng, N, cs.S, cs.firstFrame, stream_);
+        const bool sharded = cs.shardGlobalN > 0;        // stream ids of an ommatidium-range shard use global indices
+        launchRngInit(cs.dRng, N, cs.S, cs.firstFrame, sharded ? cs.shardGlobalN : static_cast<unsigned long long>(N),
+                      sharded ? cs.shardFirst : 0ull, stream_);
         launches_++;
         cs.frameIndex = cs.firstFrame;
         cs.randomsConfigured = true;

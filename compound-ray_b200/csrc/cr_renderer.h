@@ -32,6 +32,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     bool randomsConfigured = false;    // cameras/CompoundEyeDataTypes.h:12
     uint64_t frameIndex = 0;           // frames rendered since the streams were (re)initialised
     uint64_t firstFrame = 0;           // frame offset applied at the next stream initialisation
+    uint64_t shardGlobalN = 0, shardFirst = 0;   // ommatidium-range shard: rows [shardFirst, shardFirst+N) of shardGlobalN (0 = whole eye)
     // multi-frame batch buffers (crRenderPoseBatch)
     float* dBatchSamples = nullptr; float4* dBatchSummed = nullptr; DevicePose* dBatchPoses = nullptr;
     size_t batchSampleCap = 0, batchSummedCap = 0, batchPoseCap = 0;
@@ -78,6 +79,7 @@ public:
     void copyOmmatidialData(float* outRgb);                       // float RGB per ommatidium of the last frame
     double renderPoseBatch(const float* poses12, size_t count, unsigned char* outRgba, void* outDevice);
     void setFirstFrame(uint64_t k);
+    void setOmmatidialShard(uint64_t globalCount, uint64_t first);
     double lastTraceMs() const { return lastTraceMs_; }
     unsigned long long launchCount() const { return launches_; }
     double bvhBuildMs() const { return bvh_.buildMs; }

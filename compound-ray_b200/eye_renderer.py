@@ -106,6 +106,7 @@ def configureFunctions(eyeRenderer):
     r.crRenderPoseBatch.argtypes = [vp, C.c_size_t, vp, vp]
     r.crRenderPoseBatch.restype = C.c_double
     r.crSetFirstFrame.argtypes = [C.c_uint64]
+    r.crSetOmmatidialShard.argtypes = [C.c_uint64, C.c_uint64]
     r.crGetLastTraceMs.restype = C.c_double
     r.crGetLaunchCount.restype = C.c_ulonglong
     r.crGetBvhBuildMs.restype = C.c_double

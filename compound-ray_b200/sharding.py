@@ -1,4 +1,4 @@
-"""Pose sharding across GPUs -- host-side logic only, no device code.
+"""Pose sharding and ommatidium-range sharding across GPUs -- host-side logic only, no device code.
 
 The path shards by camera pose: rank r of R renders the contiguous pose block
 [lo, hi) of a P-pose run; scene, BVH and eye are replicated per GPU; the only exchange is the
@@ -43,3 +43,37 @@ def unpad(gathered, world: int, n_poses: int):
         return np.concatenate(parts, axis=0)
     import torch
     return torch.cat(parts, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Secondary partition: one pose, large N*S -- rank r owns the ommatidium rows [lo, hi) of the eye.
+# Stream ids keep the GLOBAL indices (crSetOmmatidialShard), so the gathered per-ommatidium RGB
+# equals the unsharded frame bit for bit; projection runs after the gather.
+# ---------------------------------------------------------------------------------------------
+def ommatidia_block(rank: int, world: int, n_ommatidia: int) -> tuple[int, int]:
+    """Contiguous block of ommatidium rows for `rank` (same rule as pose_block)."""
+    return pose_block(rank, world, n_ommatidia)
+
+
+def configure_ommatidia_shard(lib, er, ommatidia, rank: int, world: int):
+    """Give this rank its rows of `ommatidia` (float32[N][8]) and declare the shard to the library.
+    Returns (lo, hi).  Call setCurrentEyeSamplesPerOmmatidium before or after; both reset the streams."""
+    lo, hi = ommatidia_block(rank, world, len(ommatidia))
+    er.setOmmatidiaFromArray(lib, ommatidia[lo:hi])
+    lib.crSetOmmatidialShard(len(ommatidia), lo)
+    return lo, hi
+
+
+def allgather_rows(local_rows, world: int, n_total: int, dist=None):
+    """Allgather equally padded per-rank row blocks ([rows, ...] torch tensor) -> [n_total, ...]."""
+    import torch
+    blk = padded_block_size(world, n_total)
+    send = torch.zeros((blk,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    send[: local_rows.shape[0]] = local_rows
+    if world == 1:
+        return send[:n_total]
+    if dist is None:
+        import torch.distributed as dist
+    gathered = torch.zeros((world * blk,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
+    return unpad(gathered, world, n_total)

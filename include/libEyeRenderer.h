@@ -104,6 +104,11 @@ double crRenderPoseBatch(const float* poses, size_t count, unsigned char* outHos
 /* Position the RNG streams as if `frame` frames had already been rendered (pose sharding/restart);
  * takes effect at the next stream initialisation, which this call forces. */
 void crSetFirstFrame(uint64_t frame);
+/* Ommatidium-range sharding (one pose, large N*S; SURVEY 8e secondary partition): declare that the rows given to
+ * setOmmatidia are rows [firstIndex, firstIndex+count) of an eye of globalCount ommatidia.  Sample stream ids then
+ * use the global indices (id = globalCount*s + firstIndex + o, shaders.cu:680-685), so the gathered per-ommatidium
+ * results equal the unsharded frame bit for bit.  globalCount = 0 switches back.  Forces a stream initialisation. */
+void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex);
 /* CUDA-event time of the last compound trace launch(es), milliseconds. */
 double crGetLastTraceMs(void);
 /* Kernels launched by this library so far. */

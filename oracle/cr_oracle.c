@@ -195,6 +195,25 @@ API void cro_position_streams(xw_state* states, int64_t N, int64_t S, unsigned l
     }
 }
 
+/* Ommatidium-range shard (secondary partition): the local table holds rows
+ * [o_first, o_first+N) of an eye of n_global ommatidia; local slot N*s+o carries the stream of the
+ * GLOBAL id n_global*s + o_first + o (shaders.cu:680-685 with global indices). */
+API void cro_position_streams_shard(xw_state* states, int64_t N, int64_t S, unsigned long long first_frame,
+                                    unsigned long long n_global, unsigned long long o_first)
+{
+    cro_xorwow_build_tables();
+    #pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < N * S; k++) {
+        const int64_t s = k / N, o = k - s * N;
+        xw_state st;
+        cro_xorwow_init(&st, 42ull, n_global * (unsigned long long)s + o_first + (unsigned long long)o, 0ull);
+        const unsigned long long even = first_frame & ~1ull;
+        if (even) cro_xorwow_skipahead(&st, 2ull * even);
+        if (first_frame & 1ull) { (void)cro_xorwow_normal(&st); (void)cro_xorwow_uniform(&st); }
+        states[k] = st;
+    }
+}
+
 /* =====================================================================================
  *  2. Ommatidial sample rays   (libEyeRenderer3/shaders.cu:648-662, 664-709)
  * ===================================================================================== */

@@ -81,6 +81,7 @@ def lib():
         L.cro_draws_before_frame.argtypes = [C.c_ulonglong]
         L.cro_draws_before_frame.restype = C.c_ulonglong
         L.cro_position_streams.argtypes = [vp, i64, i64, C.c_ulonglong]
+        L.cro_position_streams_shard.argtypes = [vp, i64, i64, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]
         L.cro_generate_rays.argtypes = [vp, i64, i64, C.POINTER(Pose), vp, C.c_int, vp, vp, vp]
         L.cro_trace_bruteforce.argtypes = [vp, i64, vp, vp, vp, i64, f32, vp]
         L.cro_bvh_build.argtypes = [vp, i64]
@@ -283,6 +284,14 @@ class CompoundEyeOracle:
         """Position every stream as if k frames had been rendered (pose sharding / restart)."""
         self.states = np.zeros(len(self.omm) * self.S, dtype=STATE_DTYPE)
         lib().cro_position_streams(_p(self.states), len(self.omm), self.S, int(k))
+        self.configured = True
+
+    def set_shard(self, n_global, o_first, first_frame=0):
+        """The table holds rows [o_first, o_first+N) of an eye of n_global ommatidia: streams keep their
+        global ids (== crSetOmmatidialShard in the product)."""
+        self.states = np.zeros(len(self.omm) * self.S, dtype=STATE_DTYPE)
+        lib().cro_position_streams_shard(_p(self.states), len(self.omm), self.S, C.c_ulonglong(int(first_frame)),
+                                         C.c_ulonglong(int(n_global)), C.c_ulonglong(int(o_first)))
         self.configured = True
 
     def set_render_size(self, w, h):

@@ -136,6 +136,47 @@ def test_entry_frontier_equals_root_traversal(lib, er, terrain):
     assert visits[1, 0] < visits[0, 0], "the frontier must only remove node fetches"
 
 
+def test_ommatidium_range_shards_equal_the_whole_eye(lib, er, loader, oracle, terrain):
+    """crSetOmmatidialShard: three uneven ommatidium ranges rendered one after another reproduce the per-ommatidium
+    float RGB and 8-bit rows of the unsharded eye bit for bit (frames 0 and 1), and shard 1 equals the oracle."""
+    import sharding
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    sc, sh, ocam = load_oracle_scene(loader, oracle, terrain, "compound-cam")
+    omm = np.asarray(ocam.ommatidia, np.float32).reshape(-1, 8)[:1001].copy()
+    N, S = len(omm), 16
+    er.setOmmatidiaFromArray(lib, omm)
+    lib.crSetOmmatidialShard(0, 0)
+    er.setRenderSize(lib, N, 1)
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    whole = []
+    for frame in range(2):
+        lib.renderFrame()
+        whole.append((er.getOmmatidialData(lib).copy(), er.getFrame(lib, N, 1).copy()))
+    world = 3
+    parts = [[], []]
+    for rank in range(world):
+        lo, hi = sharding.configure_ommatidia_shard(lib, er, omm, rank, world)
+        er.setRenderSize(lib, hi - lo, 1)
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
+        if rank == 1:
+            eye = oracle.CompoundEyeOracle(sh, omm[lo:hi], oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+            eye.set_shard(N, lo)
+        for frame in range(2):
+            lib.renderFrame()
+            rgb = er.getOmmatidialData(lib).copy()
+            parts[frame].append((rgb, er.getFrame(lib, hi - lo, 1).copy()))
+            if rank == 1:
+                eye.render_frame(method="bvh", project=False)
+                assert np.array_equal(rgb.view(np.uint32), eye.last["summed"].view(np.uint32))
+    lib.crSetOmmatidialShard(0, 0)
+    for frame in range(2):
+        rgb = np.concatenate([p[0] for p in parts[frame]]); row = np.concatenate([p[1] for p in parts[frame]], axis=1)
+        assert np.array_equal(rgb.view(np.uint32), whole[frame][0].view(np.uint32)), f"frame {frame} RGB"
+        assert np.array_equal(row, whole[frame][1]), f"frame {frame} row"
+
+
 def test_cfg4_full_sample_count_properties(lib, er, terrain):
     """S=1024 on the headline workload (10.24M rays/frame): the batch path, the per-frame ABI and a
     restarted (sharded) run produce byte-identical rows."""

@@ -74,3 +74,52 @@ def test_sharded_run_equals_sequential_run(ref_data, oracle, loader, tmp_path):
     for p in range(P):
         eye.pose = oracle.make_pose(positions[p], cam.x_axis, cam.y_axis, cam.z_axis)
         assert np.array_equal(r0[p], eye.render_frame(method="brute")[0]), f"pose {p}"
+
+
+def _omm_worker(rank, world, port, out_dir, data_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, PKG)
+    import torch
+    import torch.distributed as dist
+    import sharding
+    from oracle import gltf_loader, oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    path = os.path.join(data_dir, "data", "test-scene", "test-scene.gltf")
+    sc = gltf_loader.load_scene(path)
+    cam = [c for c in sc.cameras if c.name == "insect-cam-2"][0]
+    sh = O.SceneHandle(sc)
+    omm = np.asarray(cam.ommatidia, np.float32).reshape(-1, 8)
+    N, S = len(omm), 5
+    lo, hi = sharding.ommatidia_block(rank, world, N)
+    eye = O.CompoundEyeOracle(sh, omm[lo:hi], O.pose_from_camera(cam), "single_dimension_fast", samples=S)
+    eye.set_render_size(hi - lo, 1)
+    eye.set_shard(N, lo)                                       # == crSetOmmatidialShard(N, lo) in the product
+    out = []
+    for frame in range(2):
+        eye.render_frame(method="brute", project=False)
+        out.append(sharding.allgather_rows(torch.from_numpy(eye.last["summed"].copy()), world, N, dist).numpy())
+    np.save(os.path.join(out_dir, f"omm_rank{rank}.npy"), np.stack(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ommatidium_range_shards_equal_the_whole_eye(ref_data, oracle, loader, tmp_path):
+    """SURVEY 8e secondary partition: ranks own ommatidium ranges of ONE pose; stream ids stay global, so the
+    allgathered per-ommatidium float RGB equals the unsharded frame bit for bit (frames 0 and 1)."""
+    import sharding
+    import torch.multiprocessing as mp
+    for world in (2, 3, 7):
+        blocks = [sharding.ommatidia_block(r, world, 100) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == 100 and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mp.spawn(_omm_worker, args=(world, port, str(tmp_path), ref_data), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "omm_rank0.npy"); r1 = np.load(tmp_path / "omm_rank1.npy")
+    assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32)), "every rank holds the full result"
+    path = os.path.join(ref_data, "data", "test-scene", "test-scene.gltf")
+    sc = loader.load_scene(path)
+    cam = [c for c in sc.cameras if c.name == "insect-cam-2"][0]
+    eye = oracle.CompoundEyeOracle(oracle.SceneHandle(sc), cam.ommatidia, oracle.pose_from_camera(cam), "single_dimension_fast", samples=5)
+    for frame in range(2):
+        eye.render_frame(method="brute", project=False)
+        assert np.array_equal(r0[frame].view(np.uint32), eye.last["summed"].view(np.uint32)), f"frame {frame}"
