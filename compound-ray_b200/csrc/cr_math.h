@@ -124,8 +124,56 @@ CR_HD float exp(float x)
 }
 
 // x^y for x >= 0 (gamma 2.2 and 1/2.2 only: shaders.cu:100-106,183-187)
+CR_HD float powGeneric(float x, float y)      // the definition: exp(y * log(x)) with the special cases
+{
+    if (x != x || y != y) return NAN;
+    if (x == 0.0f) return (y > 0.0f) ? 0.0f : ((y == 0.0f) ? 1.0f : INFINITY);
+    if (x < 0.0f) return NAN;
+    return crm::exp(y * crm::log(x));
+}
 CR_HD float pow(float x, float y)
 {
+    // Fast path for the values this renderer actually raises (colours, gamma 2.2 and 1/2.2): normal x in
+    // [2^-40, 2^40] and |y| <= 2.5, so |y*log x| < 70.  It performs EXACTLY the operations of
+    // exp(y * log(x)) below with the branches that cannot be taken in that range removed (no NaN/zero/
+    // denormal/overflow cases; the 2^n scaling is one exponent add instead of two exact multiplies), hence
+    // the same bits -- checked exhaustively over the whole range by tests/test_host.py.
+    const uint32_t ux = f2u(x);
+    if (ux - 0x2B800000u <= 0x28000000u && fabsf(y) <= 2.5f) {
+        int e = static_cast<int>(ux >> 23) - 126;
+        float m = u2f((ux & 0x007fffffu) | 0x3f000000u);
+        if (m < 0.70710678118654752440f) { e -= 1; m = (m + m) - 1.0f; }
+        else { m = m - 1.0f; }
+        const float z = m * m;
+        float p = 7.0376836292e-2f;
+        p = fmaf(p, m, -1.1514610310e-1f);
+        p = fmaf(p, m, 1.1676998740e-1f);
+        p = fmaf(p, m, -1.2420140846e-1f);
+        p = fmaf(p, m, 1.4249322787e-1f);
+        p = fmaf(p, m, -1.6668057665e-1f);
+        p = fmaf(p, m, 2.0000714765e-1f);
+        p = fmaf(p, m, -2.4999993993e-1f);
+        p = fmaf(p, m, 3.3333331174e-1f);
+        float l = (m * z) * p;
+        const float fe = static_cast<float>(e);
+        l = fmaf(fe, -2.12194440e-4f, l);
+        l = fmaf(-0.5f, z, l);
+        float lg = m + l;
+        lg = fmaf(fe, 0.693359375f, lg);
+        const float t = y * lg;
+        const float n = floorf(fmaf(t, 1.44269504088896341f, 0.5f));
+        float r = fmaf(n, -0.693359375f, t);
+        r = fmaf(n, 2.12194440e-4f, r);
+        const float zz = r * r;
+        float q = 1.9875691500e-4f;
+        q = fmaf(q, r, 1.3981999507e-3f);
+        q = fmaf(q, r, 8.3334519073e-3f);
+        q = fmaf(q, r, 4.1665795894e-2f);
+        q = fmaf(q, r, 1.6666665459e-1f);
+        q = fmaf(q, r, 5.0000001201e-1f);
+        const float v = fmaf(q, zz, r) + 1.0f;
+        return u2f(f2u(v) + (static_cast<uint32_t>(static_cast<int>(n)) << 23));
+    }
     if (x != x || y != y) return NAN;
     if (x == 0.0f) return (y > 0.0f) ? 0.0f : ((y == 0.0f) ? 1.0f : INFINITY);
     if (x < 0.0f) return NAN;

@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, PKG
 
 
 def _declared_symbols():
@@ -327,3 +327,14 @@ def test_scene_with_external_jpeg_texture(lib, tmp_path):
     info = np.zeros((1, 4), np.int32)
     lib.crDebugCopyMeshInfo(info.ctypes.data, None)
     assert info[0, 1] == 1 and info[0, 2] == 0                       # has UVs, texture 0
+
+
+def test_pow_fast_path_equals_its_definition(tmp_path):
+    """crm::pow's branch-free fast path (colours, gamma 2.2 and 1/2.2) must return the bits of exp(y*log(x)),
+    the definition the oracle evaluates: compiled from the product header and compared on the host."""
+    import subprocess
+    exe = str(tmp_path / "powchk")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fopenmp", "-march=x86-64-v3",
+                    "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "pow_fastpath_check.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
