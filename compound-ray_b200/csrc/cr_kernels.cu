@@ -427,7 +427,11 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 // Rays drawn outside kConeSigmas, eyes whose axes are not unit length, poses that are not
 // orthonormal (then the bound above does not hold) and cones wider than 1 rad start at the root.
 // ------------------------------------------------------------------------------------------
-constexpr int kEntryK = 4;
+#ifndef CR_ENTRY_BUDGET
+#define CR_ENTRY_BUDGET 4
+#endif
+constexpr int kEntryK = 4;                      // slots of the int4 record
+constexpr int kEntryBudget = CR_ENTRY_BUDGET;   // entries actually handed out (<= kEntryK)
 
 struct ConePyramid { V3 apex, axis, n0, n1, n2, n3; };
 
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
                 const int cnt = ((fl >> 1) & 1) + ((fl >> 2) & 1);
                 const bool wasFin = (L.fin >> i) & 1u;
                 if (!(fl & 1)) entryAppend(Nw, L.ref[i], L.key[i], wasFin);
-                else if ((fl & 8) || Nw.n + cnt + (nOld - 1 - i) > kEntryK) entryAppend(Nw, L.ref[i], L.key[i], true);
+                else if ((fl & 8) || Nw.n + cnt + (nOld - 1 - i) > kEntryBudget) entryAppend(Nw, L.ref[i], L.key[i], true);
                 else {
                     if (fl & 2) entryAppend(Nw, c0, q0, false);
                     if (fl & 4) entryAppend(Nw, c1, q1, false);
