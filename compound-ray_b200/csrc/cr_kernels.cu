@@ -425,7 +425,8 @@ __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shad
 // square pyramid circumscribing the cone widened by 1 % + 1 mrad (orders of magnitude above the
 // rounding of either test), so no ray of the cone could have passed the slab test of that box.
 // Rays drawn outside kConeSigmas, eyes whose axes are not unit length, poses that are not
-// orthonormal (then the bound above does not hold) and cones wider than 1 rad start at the root.
+// orthonormal (then the bound above does not hold), negative focal offsets (tmin < 0 admits hits behind
+// the origin) and cones wider than 1 rad start at the root.
 // ------------------------------------------------------------------------------------------
 #ifndef CR_ENTRY_BUDGET
 #define CR_ENTRY_BUDGET 4
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     const float half = p2.w * 1.01f + 1.0e-3f;
     const float tolU = 1.0e-4f;
     bool ok = live && half <= 1.0f;
+    ok = ok && p1.w >= 0.0f;                    // tmin = focal offset < 0 lets a ray hit geometry BEHIND its origin: no forward cone
     ok = ok && fabsf(vdot(a, a) - 1.0f) <= tolU;
     ok = ok && fabsf(vdot(X, X) - 1.0f) <= tolU && fabsf(vdot(Y, Y) - 1.0f) <= tolU && fabsf(vdot(Z, Z) - 1.0f) <= tolU;
     ok = ok && fabsf(vdot(X, Y)) <= tolU && fabsf(vdot(X, Z)) <= tolU && fabsf(vdot(Y, Z)) <= tolU;

@@ -74,7 +74,7 @@ def _stress_eye(n, seed):
     omm[:, 0:3] = d * 0.05 + rng.normal(scale=0.01, size=(n, 3))
     omm[:, 3:6] = d
     omm[:, 6] = np.radians(rng.choice([0.0, 0.05, 1.0, 2.3, 8.0, 20.0, 35.0, 60.0, 120.0], size=n))
-    omm[:, 7] = rng.choice([0.0, 0.0, 0.01, 0.5, -0.2], size=n)
+    omm[:, 7] = rng.choice([0.0, 0.0, 0.01, 0.5, -0.2, -8.0], size=n)   # negative: tmin < 0, hits behind the origin count
     omm[0, 3:6] = (0, 1, 0); omm[1, 3:6] = (0, -1, 0)
     omm[2, 3:6] = (0.6, 0.52915026, 0.6)                 # az == ax: perp falls back to (0,0,1), not perpendicular
     omm[3:40, 3:6] *= rng.uniform(0.5, 2.0, size=(37, 1)).astype(np.float32)   # non-unit axes
