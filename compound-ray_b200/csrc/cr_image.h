@@ -3,7 +3,7 @@
 // image reaches MulticamScene::addImage (libEyeRenderer3/MulticamScene.cpp:753-798) as 4-channel
 // 8-bit RGBA, row 0 first.  Only the formats the shipped scenes use are implemented here:
 // non-interlaced PNG, bit depth 8 (grey, grey+alpha, RGB, RGBA, palette) and 16 (reduced to the
-// high byte), and baseline JPEG (cr_jpeg.h).
+// high byte), and baseline + progressive JPEG (cr_jpeg.h).
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -1,4 +1,4 @@
-// cr_jpeg.h -- baseline JPEG (SOF0/SOF1, 8-bit, Huffman) decoder to RGBA8.
+// cr_jpeg.h -- baseline and progressive JPEG (SOF0/SOF1/SOF2, 8-bit, Huffman) decoder to RGBA8.
 //
 // The reference decodes textures through tinygltf -> stb_image with req_comp = 4
 // (support/tinygltf/stb_image.h; call site libEyeRenderer3/MulticamScene.cpp:584-600), e.g. the
@@ -10,9 +10,12 @@
 //     (3*t0 + t1 + 8) >> 4 in 2-D, pixel-replication for other ratios;
 //   * JFIF YCbCr -> RGB in 20-bit fixed point with 12-bit constants (R = Y + 1.402 Cr, ...), the green
 //     chroma-blue product truncated to 16 bits as in the SIMD-compatible formulation.
-// Progressive (SOF2) and arithmetic-coded streams are rejected with an error.
+// Progressive streams (ITU-T T.81 Annex G: spectral selection + successive approximation, DC scans
+// interleaved or not, AC scans per component with end-of-band runs) accumulate coefficients over all
+// scans and are dequantised + inverse-transformed once at the end, over the blocks that cover the
+// component's real extent, as stb_image does.  Arithmetic-coded streams are rejected with an error.
 // Pinned by tests/golden/stb_jpeg_kat.json (oracle/kat/stb_kat.cpp compiled against the reference's
-// stb_image.h): byte-exact on 4:4:4, 4:2:2, 4:2:0 and greyscale streams.
+// stb_image.h): byte-exact on 4:4:4, 4:2:2, 4:2:0 and greyscale streams, baseline and progressive.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -40,6 +43,7 @@ struct Component {
     int w = 0, hgt = 0;                // meaningful samples: ceil(img * h / hmax)
     int dcPred = 0;
     std::vector<uint8_t> plane;
+    std::vector<short> coef;           // progressive: blocksW*blocksH*64 coefficients in natural order, before dequantisation
 };
 
 class Decoder {
@@ -55,7 +59,7 @@ public:
             const int m = nextMarker();
             switch (m) {
                 case 0xC0: case 0xC1: frameHeader(); break;
-                case 0xC2: fail("progressive JPEG is not supported (baseline only)");
+                case 0xC2: progressive_ = true; frameHeader(); break;
                 case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
                     fail("unsupported JPEG coding process");
                 case 0xC4: huffmanTables(); break;
@@ -73,6 +77,7 @@ public:
             if (p_ >= end_ && !done) { if (scanned_) break; fail("truncated JPEG"); }
         }
         if (!scanned_) fail("JPEG without image data");
+        if (progressive_) finishProgressive();
         return assemble();
     }
 
@@ -185,6 +190,7 @@ private:
             c.stride = c.blocksW * 8;
             c.rows = c.blocksH * 8;
             c.plane.assign(static_cast<size_t>(c.stride) * static_cast<size_t>(c.rows), 0);
+            if (progressive_) c.coef.assign(static_cast<size_t>(c.blocksW) * static_cast<size_t>(c.blocksH) * 64, 0);
         }
         haveFrame_ = true;
     }
@@ -260,9 +266,169 @@ private:
             }
         }
     }
+    // ---- progressive scans (T.81 Annex G) -----------------------------------------------------------
+    int getBits(int n)
+    {
+        if (bitCount_ < n) fillBits();
+        const int v = static_cast<int>(bitBuf_ >> (32 - n));
+        bitBuf_ <<= n; bitCount_ -= n;
+        return v;
+    }
+    void progressiveDC(Component& c, short* d, int Ah, int Al)
+    {
+        if (Ah == 0) {                                  // first pass: the DC difference, scaled by the point transform
+            const Huffman& hd = dc_[c.td];
+            if (!hd.present) fail("missing Huffman table");
+            const int t = decodeSymbol(hd);
+            if (t > 16) fail("bad DC code");
+            c.dcPred += t ? receiveExtend(t) : 0;
+            d[0] = static_cast<short>(c.dcPred * (1 << Al));
+        } else if (getBits(1)) {                        // refinement: one more bit of precision
+            d[0] = static_cast<short>(d[0] + (1 << Al));
+        }
+    }
+    void refineNonZero(short* q, int bit)               // correction bit for a coefficient with history
+    {
+        if (getBits(1) && (*q & bit) == 0) *q = static_cast<short>(*q > 0 ? *q + bit : *q - bit);
+    }
+    void progressiveAC(Component& c, short* d, int Ss, int Se, int Ah, int Al)
+    {
+        const Huffman& ha = ac_[c.ta];
+        if (!ha.present) fail("missing Huffman table");
+        if (Ah == 0) {                                  // first pass over the band Ss..Se
+            if (eobRun_) { --eobRun_; return; }
+            for (int k = Ss; k <= Se;) {
+                const int rs = decodeSymbol(ha);
+                const int r = rs >> 4, sz = rs & 15;
+                if (sz == 0) {
+                    if (r < 15) {                       // EOBn: this and the next 2^r + extra - 1 blocks are finished
+                        eobRun_ = 1 << r;
+                        if (r) eobRun_ += getBits(r);
+                        --eobRun_;
+                        break;
+                    }
+                    k += 16;                            // ZRL
+                } else {
+                    k += r;
+                    if (k > 63) fail("bad AC run");
+                    d[kZigzag[k++]] = static_cast<short>(receiveExtend(sz) * (1 << Al));
+                }
+            }
+            return;
+        }
+        const int bit = 1 << Al;                        // refinement pass
+        if (eobRun_) {
+            --eobRun_;
+            for (int k = Ss; k <= Se; k++) { short* q = &d[kZigzag[k]]; if (*q != 0) refineNonZero(q, bit); }
+            return;
+        }
+        for (int k = Ss; k <= Se;) {
+            const int rs = decodeSymbol(ha);
+            int r = rs >> 4, sz = rs & 15, value = 0;
+            if (sz == 0) {
+                if (r < 15) {                           // EOBn: the rest of this band only receives correction bits
+                    eobRun_ = (1 << r) - 1;
+                    if (r) eobRun_ += getBits(r);
+                    r = 64;
+                }                                       // else ZRL: skip 16 zero-history coefficients
+            } else {
+                if (sz != 1) fail("bad refinement code");
+                value = getBits(1) ? bit : -bit;        // a new coefficient of magnitude 1 << Al
+            }
+            while (k <= Se) {                           // r counts zero-history coefficients only
+                short* q = &d[kZigzag[k++]];
+                if (*q != 0) refineNonZero(q, bit);
+                else if (r == 0) { *q = static_cast<short>(value); break; }
+                else --r;
+            }
+        }
+    }
+    // true: keep going; false: a marker other than RSTn ended the scan
+    bool restartBoundary(int& todo)
+    {
+        if (--todo > 0) return true;
+        if (!hitMarker_) {
+            bitCount_ = 0; bitBuf_ = 0;
+            if (p_ + 1 < end_ && p_[0] == 0xFF && p_[1] >= 0xD0 && p_[1] <= 0xD7) p_ += 2;
+        } else if (!(marker_ >= 0xD0 && marker_ <= 0xD7)) {
+            return false;
+        }
+        resetEntropy();
+        eobRun_ = 0;
+        todo = restartInterval_;
+        return true;
+    }
+    void scanProgressive()
+    {
+        const int len = be16();
+        const int n = byte();
+        if (n < 1 || n > static_cast<int>(comps_.size()) || len != 6 + 2 * n) fail("bad SOS");
+        int order[4];
+        for (int i = 0; i < n; i++) {
+            const int id = byte(), q = byte();
+            int which = -1;
+            for (size_t j = 0; j < comps_.size(); j++) if (comps_[j].id == id) which = static_cast<int>(j);
+            if (which < 0) fail("scan names an unknown component");
+            order[i] = which;
+            comps_[static_cast<size_t>(which)].td = q >> 4;
+            comps_[static_cast<size_t>(which)].ta = q & 15;
+            if ((q >> 4) > 3 || (q & 15) > 3) fail("bad table selector");
+        }
+        const int Ss = byte(), Se = byte(), a = byte();
+        const int Ah = a >> 4, Al = a & 15;
+        if (Ss > 63 || Se > 63 || Ss > Se || Ah > 13 || Al > 13) fail("bad progressive scan parameters");
+        if (Ss == 0 && Se != 0) fail("a progressive scan cannot mix DC and AC coefficients");
+        if (Ss != 0 && n != 1) fail("progressive AC scans carry one component");
+        resetEntropy();
+        eobRun_ = 0;
+        int todo = restartInterval_ ? restartInterval_ : 0x7fffffff;
+        bool go = true;
+        if (n == 1) {                                   // non-interleaved: the component's own block raster, real extent only
+            Component& c = comps_[static_cast<size_t>(order[0])];
+            const int bw = (c.w + 7) >> 3, bh = (c.hgt + 7) >> 3;
+            for (int j = 0; j < bh && go; j++)
+                for (int i = 0; i < bw && go; i++) {
+                    short* d = &c.coef[64 * (static_cast<size_t>(i) + static_cast<size_t>(j) * static_cast<size_t>(c.blocksW))];
+                    if (Ss == 0) progressiveDC(c, d, Ah, Al); else progressiveAC(c, d, Ss, Se, Ah, Al);
+                    go = restartBoundary(todo);
+                }
+        } else {                                        // interleaved DC scan: MCU order
+            for (int my = 0; my < mcusY_ && go; my++)
+                for (int mx = 0; mx < mcusX_ && go; mx++) {
+                    for (int k = 0; k < n; k++) {
+                        Component& c = comps_[static_cast<size_t>(order[k])];
+                        for (int by = 0; by < c.v; by++)
+                            for (int bx = 0; bx < c.h; bx++) {
+                                const size_t x2 = static_cast<size_t>(mx * c.h + bx), y2 = static_cast<size_t>(my * c.v + by);
+                                progressiveDC(c, &c.coef[64 * (x2 + y2 * static_cast<size_t>(c.blocksW))], Ah, Al);
+                            }
+                    }
+                    go = restartBoundary(todo);
+                }
+        }
+        scanned_ = true;
+        if (hitMarker_ && marker_ == 0xD9) p_ = end_;
+        else if (hitMarker_) p_ -= 2;
+    }
+    void finishProgressive()
+    {
+        short blk[64];
+        for (auto& c : comps_) {
+            const uint16_t* dq = dequant_[c.tq];
+            const int bw = (c.w + 7) >> 3, bh = (c.hgt + 7) >> 3;
+            for (int j = 0; j < bh; j++)
+                for (int i = 0; i < bw; i++) {
+                    const short* d = &c.coef[64 * (static_cast<size_t>(i) + static_cast<size_t>(j) * static_cast<size_t>(c.blocksW))];
+                    for (int k = 0; k < 64; k++) blk[k] = static_cast<short>(d[k] * dq[k]);
+                    idct(blk, &c.plane[static_cast<size_t>(j) * 8 * static_cast<size_t>(c.stride) + static_cast<size_t>(i) * 8], c.stride);
+                }
+        }
+    }
+
     void scan()
     {
         if (!haveFrame_) fail("SOS before SOF");
+        if (progressive_) { scanProgressive(); return; }
         const int len = be16();
         const int n = byte();
         if (n != static_cast<int>(comps_.size()) || len != 6 + 2 * n) fail("only single, fully interleaved scans are supported");
@@ -468,7 +634,8 @@ private:
     const uint8_t* end_;
     int W_ = 0, H_ = 0, hmax_ = 1, vmax_ = 1, mcuW_ = 8, mcuH_ = 8, mcusX_ = 0, mcusY_ = 0;
     int restartInterval_ = 0;
-    bool haveFrame_ = false, scanned_ = false, jfif_ = false;
+    bool haveFrame_ = false, scanned_ = false, jfif_ = false, progressive_ = false;
+    int eobRun_ = 0;                   // progressive: blocks still covered by the last end-of-band run
     int adobeTransform_ = -1;
     std::vector<Component> comps_;
     uint16_t dequant_[4][64] = {};

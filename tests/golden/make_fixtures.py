@@ -61,6 +61,17 @@ def make_jpeg_kat():
     save("pixel_420.jpg", np.full((1, 1, 3), (200, 30, 90), np.uint8), quality=90, subsampling=2)
     save("tex_420_optimized.jpg", crop, quality=70, subsampling=2, optimize=True)
     save("tex_progressive.jpg", crop, quality=70, progressive=True)
+    # progressive streams (SOF2): spectral selection + successive approximation as written by libjpeg(-turbo)
+    save("prog_444_q90.jpg", crop, quality=90, subsampling=0, progressive=True)
+    save("prog_422_q75.jpg", crop, quality=75, subsampling=1, progressive=True)
+    save("prog_420_odd_q85.jpg", np.ascontiguousarray(tex[3:80, 5:136]), quality=85, subsampling=2, progressive=True)
+    save("prog_noise_420_q95.jpg", noise, quality=95, subsampling=2, progressive=True, optimize=True)
+    save("prog_noise_444_q30.jpg", noise, quality=30, subsampling=0, progressive=True)
+    save("prog_pixel_420.jpg", np.full((1, 1, 3), (200, 30, 90), np.uint8), quality=90, subsampling=2, progressive=True)
+    save("prog_420_restart.jpg", crop, quality=80, subsampling=2, progressive=True, restart_marker_blocks=3)
+    save("base_420_restart.jpg", crop, quality=80, subsampling=2, restart_marker_rows=1)
+    Image.fromarray(((xx * 5 + yy * 3) % 256).astype(np.uint8), "L").save(os.path.join(out, "prog_grey_q80.jpg"), format="JPEG", quality=80,
+                                                                           progressive=True)
     files = sorted(os.path.join(out, f) for f in os.listdir(out) if f.endswith(".jpg"))
     with tempfile.TemporaryDirectory() as tmp:
         idx = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "stb_kat"), tmp] + files, text=True)

@@ -274,20 +274,18 @@ def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
 
 
 def test_jpeg_decoder_matches_reference_stb_image(lib):
-    """Baseline JPEG textures decode to exactly the bytes the reference's vendored stb_image produces
+    """JPEG textures decode to exactly the bytes the reference's vendored stb_image produces
     (tests/golden/stb_jpeg_kat.npz, generated by oracle/kat/stb_kat.cpp compiled against
-    /root/reference/support/tinygltf/stb_image.h with req_comp = 4): 4:4:4, 4:2:2, 4:2:0, greyscale,
-    odd sizes, optimised Huffman tables.  Progressive streams are rejected loudly."""
+    /root/reference/support/tinygltf/stb_image.h with req_comp = 4): baseline and progressive (SOF2, spectral
+    selection + successive approximation), 4:4:4, 4:2:2, 4:2:0, greyscale, odd sizes, 1x1, optimised Huffman
+    tables, restart intervals."""
     gold = np.load(os.path.join(ROOT, "tests", "golden", "stb_jpeg_kat.npz"))
     jdir = os.path.join(ROOT, "tests", "golden", "jpeg")
     names = sorted(f for f in os.listdir(jdir) if f.endswith(".jpg"))
-    assert len(names) >= 10
+    assert len(names) >= 19 and sum(n.startswith("prog_") for n in names) >= 8
     for name in names:
         w, h = C.c_int(), C.c_int()
         ok = lib.crDebugDecodeImageFile(os.path.join(jdir, name).encode(), C.byref(w), C.byref(h))
-        if "progressive" in name:
-            assert not ok
-            continue
         assert ok, name
         px = np.zeros((h.value, w.value, 4), np.uint8)
         lib.crDebugCopyDecodedImage(px.ctypes.data)
