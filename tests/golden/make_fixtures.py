@@ -8,6 +8,8 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
   sutil_kat.json         the reference's sutil math headers evaluated on fixed inputs (oracle/_ref/sutil_kat)
   jpeg/*.jpg             small JPEG test streams written with PIL (4:4:4 / 4:2:2 / 4:2:0 / grey / progressive)
   stb_jpeg_kat.{json,npz} those streams decoded by the reference's vendored stb_image.h (oracle/_ref/stb_kat)
+  png/*.png              small PNG streams of every colour type / bit depth / tRNS form, plain and Adam7 (own writer)
+  stb_png_kat.{json,npz}  those streams decoded by the reference's vendored stb_image.h
 """
 import os
 import subprocess
@@ -84,6 +86,123 @@ def make_jpeg_kat():
         np.savez_compressed(os.path.join(HERE, "stb_jpeg_kat.npz"), **arrs)
 
 
+def _png_chunk(tag, body):
+    import struct
+    import zlib
+    return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+
+
+def write_png(path, samples, depth, ctype, interlace=False, plte=None, trns=None):
+    """Minimal PNG writer for fixtures PIL/OpenCV cannot produce (Adam7, colour keys at every depth).
+    samples: uint16 array [H][W][channels] of raw sample values; filter type cycles 0..4 over the rows."""
+    import struct
+    import zlib
+    import numpy as np
+    H, W, ch = samples.shape
+
+    def pack_rows(img):
+        h, w, _ = img.shape
+        out = bytearray()
+        prev = None
+        for y in range(h):
+            if depth == 16:
+                row = img[y].astype(">u2").tobytes()
+            elif depth == 8:
+                row = img[y].astype(np.uint8).tobytes()
+            else:
+                bits = np.unpackbits(img[y].astype(np.uint8).reshape(-1, 1), axis=1)[:, 8 - depth:].reshape(-1)
+                row = np.packbits(bits).tobytes()
+            bpp = max(1, ch * depth // 8)
+            cur = np.frombuffer(row, np.uint8).astype(np.int32)
+            up = np.zeros_like(cur) if prev is None else prev
+            left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+            ul = np.concatenate([np.zeros(bpp, np.int32), up[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+            ft = y % 5
+            if ft == 0: f = cur
+            elif ft == 1: f = cur - left
+            elif ft == 2: f = cur - up
+            elif ft == 3: f = cur - ((left + up) >> 1)
+            else:
+                pp = left + up - ul
+                pa, pb, pc = np.abs(pp - left), np.abs(pp - up), np.abs(pp - ul)
+                pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+                f = cur - pred
+            out += bytes([ft]) + (f & 255).astype(np.uint8).tobytes()
+            prev = cur
+        return bytes(out)
+
+    if interlace:
+        ox, oy, sx, sy = (0, 4, 0, 2, 0, 1, 0), (0, 0, 4, 0, 2, 0, 1), (8, 8, 4, 4, 2, 2, 1), (8, 8, 8, 4, 4, 2, 2)
+        raw = b"".join(pack_rows(samples[oy[p]::sy[p], ox[p]::sx[p]]) for p in range(7)
+                       if samples[oy[p]::sy[p], ox[p]::sx[p]].size)
+    else:
+        raw = pack_rows(samples)
+    body = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 1 if interlace else 0))
+    if plte is not None:
+        body += _png_chunk(b"PLTE", bytes(plte))
+    if trns is not None:
+        body += _png_chunk(b"tRNS", bytes(trns))
+    half = len(raw) // 2 or 1
+    z = zlib.compress(raw, 9)
+    body += _png_chunk(b"IDAT", z[:len(z) // 2]) + _png_chunk(b"IDAT", z[len(z) // 2:]) + _png_chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(body)
+
+
+def make_png_kat():
+    """png/*.png: every colour type / bit depth / tRNS form / Adam7, decoded by the reference's stb_image -> stb_png_kat.*"""
+    import json
+    import struct
+    import tempfile
+    import numpy as np
+    out = os.path.join(HERE, "png")
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(3)
+    W, H = 13, 11
+
+    def smooth(ch, maxv):
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = np.stack([(xx * (k + 2) + yy * (3 - k)) for k in range(ch)], axis=2).astype(np.float64)
+        return np.clip(base / base.max() * maxv + rng.integers(0, max(1, maxv // 8) + 1, (H, W, ch)), 0, maxv).astype(np.uint16)
+
+    pal16 = rng.integers(0, 256, 16 * 3, dtype=np.uint8)
+    pal256 = rng.integers(0, 256, 200 * 3, dtype=np.uint8)
+    for il in (False, True):
+        tagi = "_adam7" if il else ""
+        for depth in (1, 2, 4, 8, 16):
+            g = smooth(1, (1 << depth) - 1)
+            write_png(os.path.join(out, f"grey{depth}{tagi}.png"), g, depth, 0, il)
+            key = int(g[2, 3, 0])
+            write_png(os.path.join(out, f"grey{depth}_key{tagi}.png"), g, depth, 0, il, trns=struct.pack(">H", key))
+        for depth in (8, 16):
+            m = (1 << depth) - 1
+            rgb = smooth(3, m)
+            write_png(os.path.join(out, f"rgb{depth}{tagi}.png"), rgb, depth, 2, il)
+            rgb[4:6, 2:9] = rgb[0, 0]                              # a block of the key colour
+            write_png(os.path.join(out, f"rgb{depth}_key{tagi}.png"), rgb, depth, 2, il, trns=struct.pack(">HHH", *[int(v) for v in rgb[0, 0]]))
+            write_png(os.path.join(out, f"greyalpha{depth}{tagi}.png"), smooth(2, m), depth, 4, il)
+            write_png(os.path.join(out, f"rgba{depth}{tagi}.png"), smooth(4, m), depth, 6, il)
+        for depth, pal in ((1, pal16[:6]), (2, pal16[:12]), (4, pal16), (8, pal256)):
+            n = len(pal) // 3
+            idx = rng.integers(0, n, (H, W, 1)).astype(np.uint16)
+            write_png(os.path.join(out, f"pal{depth}{tagi}.png"), idx, depth, 3, il, plte=pal)
+            write_png(os.path.join(out, f"pal{depth}_trns{tagi}.png"), idx, depth, 3, il, plte=pal,
+                      trns=rng.integers(0, 256, max(1, n // 2), dtype=np.uint8))
+    for w, h in ((1, 1), (2, 3), (5, 1), (1, 9), (9, 8)):        # Adam7 passes that come out empty
+        write_png(os.path.join(out, f"tiny_{w}x{h}_adam7.png"), rng.integers(0, 256, (h, w, 3)).astype(np.uint16), 8, 2, True)
+    files = sorted(os.path.join(out, f) for f in os.listdir(out) if f.endswith(".png"))
+    with tempfile.TemporaryDirectory() as tmp:
+        idx = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "stb_kat"), tmp] + files, text=True)
+        with open(os.path.join(HERE, "stb_png_kat.json"), "w") as f:
+            f.write(idx)
+        arrs = {}
+        for name, e in json.loads(idx).items():
+            if "error" not in e:
+                arrs[name] = np.fromfile(os.path.join(tmp, name + ".rgba"), dtype=np.uint8).reshape(e["height"], e["width"], 4)
+        np.savez_compressed(os.path.join(HERE, "stb_png_kat.npz"), **arrs)
+    return len(files), len(arrs)
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
     with open(os.path.join(HERE, "xorwow_kat.json"), "w") as f:
@@ -91,6 +210,7 @@ def main():
     with open(os.path.join(HERE, "sutil_kat.json"), "w") as f:
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sutil_kat")], stdout=f)
     make_jpeg_kat()
+    make_png_kat()
     out = os.path.join(HERE, "reference_data.tar.gz")
     with tarfile.open(out, "w:gz", compresslevel=9) as tar:
         for arc, src in sorted(FILES.items()):
