@@ -303,6 +303,18 @@ void crDebugCopyBvh(float* nodes16, float* tris12)
     renderer().debugCopyBvh(nodes16, tris12);
     CR_GUARD_END()
 }
+void crDebugXorwowInit(uint64_t seed, uint64_t subsequence, uint64_t offset, uint32_t* out6)
+{
+    CR_GUARD_BEGIN
+    uint32_t d, v[5];
+    cr::xorwow::seedState(seed, d, v);
+    cr::xorwow::jumpHost(cr::Renderer::xorwowTable(), v, 0, subsequence);
+    cr::xorwow::jumpHost(cr::Renderer::xorwowTable(), v, cr::xorwow::kSeqLevels, offset);
+    d += 362437u * static_cast<uint32_t>(offset);
+    out6[0] = d;
+    for (int k = 0; k < 5; k++) out6[1 + k] = v[k];
+    CR_GUARD_END()
+}
 void crDebugSetRayDump(bool on) { renderer().dumpRays = on; }
 size_t crDebugCopyLastRayCounts(int32_t* counts2)
 {

@@ -105,7 +105,7 @@ enum Projection : int {
 
 // kernel launchers (cr_kernels.cu)
 void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal, unsigned long long oFirst,
-                   cudaStream_t stream);
+                   const uint4* jumpTable, cudaStream_t stream);
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream);
 void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream);
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);

@@ -5,7 +5,7 @@
 // written one IEEE rounding per operation with explicit fmaf() where fusion is wanted, so the CPU
 // checker reproduces rays, hits and pixel maps bit for bit (see cr_math.h).
 //
-// K0  k_rngInit            curand_init(42, id, 0) per sample stream   (shaders.cu:680-685)
+// K0  k_rngInit            curand_init(42, id, 0) per sample stream   (shaders.cu:680-685), own jump tables
 //     k_prepOmmatidia      per-ommatidium invariants of the sample-ray construction
 // K1  k_traceCompound      raygen + BVH traversal + shading, one sample ray per lane
 //                          (shaders.cu:664-731 + 110-137 + 740-811)
@@ -15,7 +15,6 @@
 //     k_projectMap         map lookup + make_color, or ids                (shaders.cu:412-640)
 // K4  k_camera             pinhole / panoramic / orthographic primary rays (shaders.cu:198-333)
 #include <cuda_runtime.h>
-#include <curand_kernel.h>
 
 #include <cstdint>
 
@@ -100,27 +99,65 @@ __device__ __forceinline__ float rngNormal(Rng& r)
 }
 
 // K0: one thread per stream.  Stream id = N*s + o (shaders.cu:668-669); stored at [o*S + s].
-// firstFrame > 0 positions the stream as if `firstFrame` frames had already been rendered
-// (pose sharding / restart): skipahead(2*floor(k/2)*... ) raw draws, plus one replayed frame when
-// k is odd so that the Box-Muller cache is populated exactly as in the sequential run.
+// v <- v * T^(n) (or T^(2^67 n) for firstLevel 0): one vector-matrix product per non-zero hex digit of n, with
+// the host-built tables of cr_xorwow_jump.h (row = 2 x 16 B: 5 words + padding).  The digits are applied from
+// the MOST significant down (the factors commute): the lanes of a warp hold consecutive ids, so they start
+// from the same seed vector and share every digit but the last -- identical bit loops and broadcast row
+// loads until the final digit, where only the matrix differs between lanes.
+__device__ __forceinline__ void xorwowJump(uint32_t& v0, uint32_t& v1, uint32_t& v2, uint32_t& v3, uint32_t& v4,
+                                           const uint4* __restrict__ table, int firstLevel, unsigned long long n)
+{
+    if (n == 0ull) return;
+    for (int k = (63 - __clzll((long long)n)) >> 2; k >= 0; k--) {
+        const int d = (int)((n >> (4 * k)) & 15ull);
+        if (!d) continue;
+        const uint4* m = table + ((size_t)(firstLevel + k) * 15 + (size_t)(d - 1)) * (160 * 2);
+        uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u, r4 = 0u;
+        const uint32_t v[5] = {v0, v1, v2, v3, v4};
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const uint4* rows = m + i * 64;
+            for (uint32_t w = v[i]; w; w &= w - 1u) {
+                const int j = __ffs((int)w) - 1;
+                const uint4 a = __ldg(rows + 2 * j);
+                const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(rows + 2 * j + 1));
+                r0 ^= a.x; r1 ^= a.y; r2 ^= a.z; r3 ^= a.w; r4 ^= b;
+            }
+        }
+        v0 = r0; v1 = r1; v2 = r2; v3 = r3; v4 = r4;
+    }
+}
+
+// K0: curand_init(42, id, 0) per sample stream (shaders.cu:680-685; curand_kernel.h:800-825) as seed
+// scrambling + one jump of id subsequences.  Threads run over ommatidia fastest, so the lanes of a warp hold
+// consecutive ids and share all but the lowest hex digit's matrix.
+// firstFrame > 0 positions the stream as if `firstFrame` frames had already been rendered (pose sharding /
+// restart): 2*(firstFrame & ~1) raw draws are skipped (3 + 1 draws per frame pair), plus one replayed frame when
+// firstFrame is odd so that the Box-Muller cache is populated exactly as in the sequential run.
 // An ommatidium-range shard (crSetOmmatidialShard) holds rows [oFirst, oFirst+N) of an eye of nGlobal
 // ommatidia: the stream id keeps the GLOBAL indices, so a sharded frame equals the unsharded one.
 __global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal,
-                          unsigned long long oFirst)
+                          unsigned long long oFirst, const uint4* __restrict__ jumpTable)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)N * S) return;
-    const int o = (int)(i / S), s = (int)(i - (long long)o * S);
+    const int s = (int)(i / N), o = (int)(i - (long long)s * N);
     const unsigned long long id = nGlobal * (unsigned long long)s + oFirst + (unsigned long long)o;
-    curandStateXORWOW_t st;
-    curand_init(42ull, id, 0ull, &st);
-    const unsigned long long evenFrames = firstFrame & ~1ull;
-    if (evenFrames) skipahead(2ull * evenFrames, &st);      // 3 + 1 draws per frame pair
+    // seed 42 (curand_kernel.h:800-812)
+    const uint32_t s0 = 42u ^ 0xaad26b49u, s1 = 0u ^ 0xf7dcefddu;
+    const uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
     Rng r;
-    r.d = st.d; r.v0 = st.v[0]; r.v1 = st.v[1]; r.v2 = st.v[2]; r.v3 = st.v[3]; r.v4 = st.v[4];
+    r.d = 6615241u + t1 + t0;
+    r.v0 = 123456789u + t0; r.v1 = 362436069u ^ t0; r.v2 = 521288629u + t1; r.v3 = 88675123u ^ t1; r.v4 = 5783321u + t0;
+    const unsigned long long skip = 2ull * (firstFrame & ~1ull);
+    if (skip) {                                                                     // same for every stream
+        xorwowJump(r.v0, r.v1, r.v2, r.v3, r.v4, jumpTable, 8, skip);
+        r.d += 362437u * (uint32_t)skip;
+    }
+    xorwowJump(r.v0, r.v1, r.v2, r.v3, r.v4, jumpTable, 0, id);                    // whole subsequences: d unchanged
     r.flag = 0; r.extra = 0.0f;
     if (firstFrame & 1ull) { (void)rngNormal(r); (void)rngUniform(r); }
-    rngStore(rng + 2 * i, r);
+    rngStore(rng + 2 * ((size_t)o * (size_t)S + (size_t)s), r);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -896,12 +933,12 @@ __global__ void k_evalMath(int fn, const float* __restrict__ a, const float* __r
 // launchers
 // ------------------------------------------------------------------------------------------
 void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal, unsigned long long oFirst,
-                   cudaStream_t stream)
+                   const uint4* jumpTable, cudaStream_t stream)
 {
     const long long n = (long long)N * S;
     if (n <= 0) return;
     const int tpb = 128;
-    k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame, nGlobal, oFirst);
+    k_rngInit<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, stream>>>(rng, N, S, firstFrame, nGlobal, oFirst, jumpTable);
 }
 
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream)

@@ -66,6 +66,12 @@ Renderer::~Renderer()
     // process teardown: the CUDA context may already be gone; do not touch the device here
 }
 
+const std::vector<uint32_t>& Renderer::xorwowTable()
+{
+    static const std::vector<uint32_t> table = xorwow::buildTable();
+    return table;
+}
+
 void Renderer::setDevice(int dev)
 {
     if (deviceReady_ && dev != device_) throw std::runtime_error("crSetDevice must be called before the first GPU use");
@@ -148,6 +154,7 @@ void Renderer::stop()
         hFrame_ = nullptr;
         frameCap_ = 0;
         frameW_ = frameH_ = 0;
+        dfree(dJumpTable_);
     }
     scene_ = HostScene();
     loaded_ = false;
@@ -364,8 +371,13 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
     }
     if (!cs.randomsConfigured) {
         const bool sharded = cs.shardGlobalN > 0;        // stream ids of an ommatidium-range shard use global indices
+        if (!dJumpTable_) {                              // XORWOW jump-ahead matrices: derived once per process (~20 ms), 1.8 MB
+            const std::vector<uint32_t>& t = xorwowTable();
+            dJumpTable_ = dallocT<uint4>(t.size() / 4);
+            CR_CUDA(cudaMemcpyAsync(dJumpTable_, t.data(), sizeof(uint32_t) * t.size(), cudaMemcpyHostToDevice, stream_));
+        }
         launchRngInit(cs.dRng, N, cs.S, cs.firstFrame, sharded ? cs.shardGlobalN : static_cast<unsigned long long>(N),
-                      sharded ? cs.shardFirst : 0ull, stream_);
+                      sharded ? cs.shardFirst : 0ull, dJumpTable_, stream_);
         launches_++;
         cs.frameIndex = cs.firstFrame;
         cs.randomsConfigured = true;

@@ -14,6 +14,7 @@
 
 #include "cr_device.h"
 #include "cr_scene.h"
+#include "cr_xorwow_jump.h"
 
 namespace cr {
 
@@ -78,6 +79,7 @@ public:
     // additive API
     void copyOmmatidialData(float* outRgb);                       // float RGB per ommatidium of the last frame
     double renderPoseBatch(const float* poses12, size_t count, unsigned char* outRgba, void* outDevice);
+    static const std::vector<uint32_t>& xorwowTable();
     void setFirstFrame(uint64_t k);
     void setOmmatidialShard(uint64_t globalCount, uint64_t first);
     double lastTraceMs() const { return lastTraceMs_; }
@@ -132,6 +134,7 @@ private:
     float2* dUvs_ = nullptr;
     float4* dColors_ = nullptr;
     MeshRec* dMeshes_ = nullptr;
+    uint4* dJumpTable_ = nullptr;                                 // cr_xorwow_jump.h tables (k_rngInit)
     std::vector<cudaArray_t> texArrays_;
     std::vector<cudaTextureObject_t> texObjects_;
 

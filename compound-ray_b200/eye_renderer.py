@@ -128,6 +128,7 @@ def configureFunctions(eyeRenderer):
     r.crDebugCopyBvh.argtypes = [vp, vp]
     r.crDebugSetRayDump.argtypes = [C.c_bool]
     r.crDebugSetEntryFrontier.argtypes = [C.c_int, C.c_int, C.c_longlong]
+    r.crDebugXorwowInit.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, vp]
     r.crDebugCopyLastRayCounts.argtypes = [vp]
     r.crDebugCopyLastRayCounts.restype = C.c_size_t
     r.crDebugCopyLastRays.argtypes = [vp, vp, vp]

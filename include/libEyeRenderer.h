@@ -138,6 +138,9 @@ void crDebugGetTextureSize(int index, int* w, int* h);
 void crDebugCopyTexture(int index, unsigned char* outRgba);   /* decoded RGBA8, row 0 first */
 size_t crDebugGetBvhNodeCount(void);
 void crDebugCopyBvh(float* nodes16, float* tris12);
+/* Host evaluation of curand_init(seed, subsequence, offset) with the library's own jump-ahead tables (the ones
+ * k_rngInit uses on the device): out6 = d, v[0..4].  No GPU needed; subsequence < 2^32. */
+void crDebugXorwowInit(uint64_t seed, uint64_t subsequence, uint64_t offset, uint32_t* out6);
 void crDebugSetRayDump(bool on);
 /* A/B switch of the per-ommatidium entry frontier (default: on for S >= 8 and N*S >= 786432 rays per frame);
  * negative thresholds keep the current value. */

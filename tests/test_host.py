@@ -353,3 +353,29 @@ def test_pow_fast_path_equals_its_definition(tmp_path):
                     "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "pow_fastpath_check.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
+
+
+def test_xorwow_jump_tables_match_curand_init(lib, oracle):
+    """The library derives its own XORWOW jump-ahead matrices (cr_xorwow_jump.h: T^(2^67) by 67 squarings, one
+    matrix per hex digit); curand_init(42, id, offset) evaluated with them on the host must equal the oracle's,
+    which is pinned to cuRAND itself by tests/golden/xorwow_kat.json.  Same tables, same routine as k_rngInit."""
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "xorwow_kat.json")))
+    out = np.zeros(6, np.uint32)
+    n_kat = 0
+    for e in kat["init"] + kat["seed_variants"]:               # states written by cuRAND's own curand_init
+        if int(e["subsequence"]) >= 2 ** 32:
+            continue
+        lib.crDebugXorwowInit(int(e["seed"]), int(e["subsequence"]), int(e["offset"]), out.ctypes.data)
+        assert [int(v) for v in out] == [int(e["d"])] + [int(v) for v in e["v"]], e
+        n_kat += 1
+    assert n_kat >= 8
+    rng = np.random.default_rng(1)
+    ids = [0, 1, 2, 15, 16, 31, 255, 256, 999, 32000, 10 ** 7, 2 ** 24 - 1, 2 ** 31 + 12345, 2 ** 32 - 1] + [int(x) for x in rng.integers(0, 2 ** 32, 200)]
+    offs = [0, 1, 2, 3, 4, 16, 12345, 2 ** 20, 2 ** 33 + 7, 2 ** 63 + 99] + [int(x) for x in rng.integers(0, 2 ** 62, 20)]
+    OL = oracle.lib()
+    for k, i in enumerate(ids):
+        for off in (offs if k < 16 else [0]):
+            st = oracle.XwState()
+            OL.cro_xorwow_init(C.byref(st), 42, i, off)
+            lib.crDebugXorwowInit(42, i, off, out.ctypes.data)
+            assert np.array_equal(out, np.array([st.d] + list(st.v), np.uint32)), (i, off)
