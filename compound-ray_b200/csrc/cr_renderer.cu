@@ -526,12 +526,12 @@ double Renderer::renderFrame()
     if (cam.kind == CAM_COMPOUND) {
         CompoundState& cs = compoundState(current_);
         prepareCompound(cs, cam);
-        CR_CUDA(cudaEventRecord(evA_, stream_));
+        if (wantTraceEvents_) CR_CUDA(cudaEventRecord(evA_, stream_));
         // single_dimension_fast: pixel x of row 0 is ommatidium x -- K1b writes the row itself
         const bool fused = projectionFromName(cam.projection) == PROJ_SINGLE_DIM_FAST && W_ > 0 && H_ > 0;
         launchCompound(cs, cam, cam.pose, fused ? dFrame_ : nullptr, fused ? std::min(cs.N, W_) : 0);
-        CR_CUDA(cudaEventRecord(evB_, stream_));
-        timedTrace = true;
+        if (wantTraceEvents_) CR_CUDA(cudaEventRecord(evB_, stream_));
+        timedTrace = wantTraceEvents_;
         if (!fused) project(cs, cam);
     } else {
         launchCamera(dscene_, static_cast<int>(cam.kind), toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
@@ -551,6 +551,8 @@ double Renderer::renderFrame()
         float k = 0.0f;
         cudaEventElapsedTime(&k, evA_, evB_);
         lastTraceMs_ = k;
+    } else {
+        lastTraceMs_ = ms;                    // no event pair requested yet: the host-side frame time
     }
     if (verbose) std::cout << "[PyEye] Rendered frame in " << ms << "ms." << std::endl;
     return ms;

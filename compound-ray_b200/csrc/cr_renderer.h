@@ -82,7 +82,7 @@ public:
     static const std::vector<uint32_t>& xorwowTable();
     void setFirstFrame(uint64_t k);
     void setOmmatidialShard(uint64_t globalCount, uint64_t first);
-    double lastTraceMs() const { return lastTraceMs_; }
+    double lastTraceMs() { wantTraceEvents_ = true; return lastTraceMs_; }   // per-frame CUDA events only once somebody asks
     unsigned long long launchCount() const { return launches_; }
     double bvhBuildMs() const { return bvh_.buildMs; }
     int lastBatchFrames() const { return lastBatchFrames_; }
@@ -149,6 +149,7 @@ private:
     int frameW_ = 0, frameH_ = 0;
 
     double lastTraceMs_ = 0.0;
+    bool wantTraceEvents_ = false;                                // renderFrame records its event pair only after crGetLastTraceMs was used
     int lastBatchFrames_ = 1;
     unsigned long long launches_ = 0;
 };

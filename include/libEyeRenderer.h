@@ -109,7 +109,8 @@ void crSetFirstFrame(uint64_t frame);
  * use the global indices (id = globalCount*s + firstIndex + o, shaders.cu:680-685), so the gathered per-ommatidium
  * results equal the unsharded frame bit for bit.  globalCount = 0 switches back.  Forces a stream initialisation. */
 void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex);
-/* CUDA-event time of the last compound trace launch(es), milliseconds. */
+/* CUDA-event time of the last compound trace launch(es), milliseconds (crRenderPoseBatch: always; renderFrame: from the
+ * first call of this function on -- until then the host-side frame time is returned, so that untimed loops pay no events). */
 double crGetLastTraceMs(void);
 /* Kernels launched by this library so far. */
 unsigned long long crGetLaunchCount(void);
