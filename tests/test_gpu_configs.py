@@ -149,6 +149,20 @@ def test_entry_frontier_fuzz(lib):
     assert res["mismatching_frames"] == 0 and res["hits"] > 50000
 
 
+def test_bvh_fuzz_against_bruteforce(lib):
+    """A slice of compound-ray_b200/tools/bvh_fuzz.py: device BVH vs the oracle's brute-force loop on random soups and
+    adversarial rays, bit-identical hits; only numerically degenerate ray/triangle pairs (|det| < 1e-5 |d||e1||e2|,
+    where binary32 Moller-Trumbore is itself off by per cent) may differ and are counted."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compound-ray_b200", "tools",
+                                                     "bvh_fuzz.py"), "--configs", "80", "--seed", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["mismatching_configs"] == 0 and res["hits"] > 50000 and res["degenerate_differences"] <= 4
+
+
 def test_ommatidium_range_shards_equal_the_whole_eye(lib, er, loader, oracle, terrain):
     """crSetOmmatidialShard: three uneven ommatidium ranges rendered one after another reproduce the per-ommatidium
     float RGB and 8-bit rows of the unsharded eye bit for bit (frames 0 and 1), and shard 1 equals the oracle."""
