@@ -7,9 +7,10 @@
 //
 // K0  k_rngInit            curand_init(42, id, 0) per sample stream   (shaders.cu:680-685), own jump tables
 //     k_prepOmmatidia      per-ommatidium invariants of the sample-ray construction
+// K0b k_buildEntries       per (frame, ommatidium): BVH subtree roots its sample cone can reach (entry frontier)
 // K1  k_traceCompound      raygen + BVH traversal + shading, one sample ray per lane
 //                          (shaders.cu:664-731 + 110-137 + 740-811)
-// K1b k_sumSamples         exact-order per-ommatidium sum (shaders.cu:341-347)
+// K1b k_sumSamples         exact-order per-ommatidium sum (shaders.cu:341-347) + 8-bit row of single_dimension_fast
 // K2  k_projectVector/Raw  single_dimension[_fast], raw_ommatidial_samples (shaders.cu:354-406)
 // K3  k_buildProjectionMap nearest-ommatidium map of the spherical modes, cached per eye/size
 //     k_projectMap         map lookup + make_color, or ids                (shaders.cu:412-640)
@@ -374,9 +375,6 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
                 cur = firstIs0 ? r0 : r1;
                 const int far = firstIs0 ? r1 : r0;
                 st.push(far);
-#ifdef CR_PREFETCH_FAR
-                if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + 4 * (size_t)far));
-#endif
             } else if (h0) cur = r0;
             else if (h1) cur = r1;
             else cur = st.pop();
