@@ -1,0 +1,36 @@
+"""Tiny tour of every kernel for compute-sanitizer (memcheck / racecheck / initcheck):
+  compute-sanitizer --tool memcheck python compound-ray_b200/tools/sanitize_run.py"""
+import os, sys, tarfile
+import numpy as np
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(_ROOT, "compound-ray_b200")); sys.path.insert(0, _ROOT)
+import eye_renderer as er
+data = os.path.join(_ROOT, "tests", "_data")
+if not os.path.exists(os.path.join(data, "data", "test-scene", "test-scene.gltf")):
+    os.makedirs(data, exist_ok=True)
+    with tarfile.open(os.path.join(_ROOT, "tests", "golden", "reference_data.tar.gz")) as tar:
+        tar.extractall(data, filter="data")
+lib = er.load_library(device=0); lib.setVerbosity(False)
+for scene, cam in (("data/test-scene/test-scene.gltf", b"insect-cam-2"), ("data/natural-standin-sky.gltf", None)):
+    lib.loadGlTFscene(os.path.join(data, scene).encode())
+    if cam: assert lib.gotoCameraByName(cam)
+    else: er.gotoFirstCompoundEye(lib)
+    N = lib.getCurrentEyeOmmatidialCount()
+    for frontier in (0, 1):
+        lib.crDebugSetEntryFrontier(frontier, 2, 0)
+        for S in (1, 5, 33, 130):                                   # partial warps, partial K1b tiles
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            for shader, size in ((b"spherical_orientationwise", (64, 48)), (b"single_dimension_fast", (N, 1)), (b"raw_ommatidial_samples", (N, S)),
+                                 (b"single_dimension", (77, 3)), (b"spherical_positionwise_ids", (40, 30))):
+                lib.setCurrentEyeShaderName(shader); er.setRenderSize(lib, *size)
+                lib.renderFrame(); lib.getFramePointer()
+            lib.setCurrentEyeShaderName(b"single_dimension_fast"); er.setRenderSize(lib, N, 1)
+            poses = er.make_poses(np.random.default_rng(S).uniform(-1, 1, (7, 3)))
+            er.renderPoseBatch(lib, poses)
+    lib.crSetFirstFrame(3); lib.renderFrame(); lib.crSetFirstFrame(0)
+    lib.crSetOmmatidialShard(5 * N, N); lib.renderFrame(); lib.crSetOmmatidialShard(0, 0)
+    lib.crDebugSetRayDump(True); lib.renderFrame(); lib.crDebugSetRayDump(False)
+    for i in range(lib.getCameraCount()):                            # ordinary cameras too
+        lib.gotoCamera(i); er.setRenderSize(lib, 50, 40); lib.renderFrame(); lib.getFramePointer()
+lib.stop()
+print("sanitize tour done")
