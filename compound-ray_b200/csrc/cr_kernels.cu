@@ -57,7 +57,7 @@ struct Rng {
 // from displacing BVH nodes in L1/L2.
 __device__ __forceinline__ Rng rngLoad(const uint4* __restrict__ p)
 {
-    const uint4 a = __ldcs(p), b = __ldcs(p + 1);
+    const uint4 a = __ldcs(p), b = __ldcs(p + 1);       // (one 256-bit streaming load measured slower here: 15.3 vs 15.5 Grays/s e2e)
     Rng r;
     r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
     r.flag = (int)b.z; r.extra = __uint_as_float(b.w);
@@ -332,6 +332,23 @@ struct Stack {
     }
 };
 
+// One 64-byte node = two 256-bit read-only loads (LDG.E.256, new with sm_100): half the load instructions and
+// half the L1 sector requests of four 128-bit loads when every lane fetches a different node.
+#ifndef CR_NODE_LDG256
+#define CR_NODE_LDG256 1
+#endif
+__device__ __forceinline__ void ldgNode(const float4* __restrict__ p, float4& n0, float4& n1, float4& n2, float4& n3)
+{
+#if CR_NODE_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(p + 2));
+#else
+    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+#endif
+}
+
 template <bool COUNT>
 __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll, size_t variantStride,
                                             const float4* __restrict__ tris, const Ray& ray, const float tmax, int* sStackLane,
@@ -362,7 +379,8 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
     for (;;) {
         while (cur >= 0) {
             const float4* np = nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            float4 n0, n1, n2, n3;
+            ldgNode(np, n0, n1, n2, n3);
             if (COUNT) nc++;
             const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), ray.tmin));
             const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), best.t));
