@@ -18,7 +18,7 @@
 //   meshes  MeshRec[nMeshes]
 // Compound eye (per camera):
 //   omm     float4[2*N]        the 32-byte ommatidium rows as loaded
-//   pre     float4[3*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp, cone bound)
+//   pre     float4[4*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp, cone bound, perp x axis, perp . axis)
 //   entries int4[F*N]          per (frame, ommatidium): up to 4 BVH subtree roots its sample cone can reach
 //                              (near to far, packed from .x, 0x80000000 = none)
 //   rng     uint4[2*N*S]       32 B compact XORWOW state per sample stream, laid out [o][s]
@@ -61,7 +61,7 @@ struct alignas(16) DevicePose {
 };
 
 struct EyeParams {
-    const float4* pre = nullptr;  // 3 float4 per ommatidium (k_prepOmmatidia)
+    const float4* pre = nullptr;  // kPreStride float4 per ommatidium (k_prepOmmatidia)
     uint4* rng = nullptr;
     float4* summed = nullptr;
     float* samples = nullptr;     // [o][s][3] per-sample colour/S
@@ -81,6 +81,7 @@ struct EyeParams {
 };
 
 constexpr int kTraceThreads = 128;
+constexpr int kPreStride = 4;     // float4 per ommatidium in the `pre` table
 constexpr float kTMax = 1e16f;
 
 struct BvhBuildResult {

@@ -186,6 +186,7 @@ struct Ray { V3 o, d; float tmin; };
 // shaders.cu:652-709 per sample):
 //   pre[0] = (relPos - normalize(axis)*focal, sd = acceptance / FWHM_SD_RATIO)
 //   pre[1] = (axis, focal)          pre[2] = (perp, kConeSigmas*|sd| = splay bound of the entry cone)
+//   pre[3] = (cross(perp, axis), dot(perp, axis))   -- rotatePoint(axis, splay, perp) without its cross and dot
 __global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* __restrict__ pre)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,13 +200,16 @@ __global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* _
     if (perp.x + perp.y + perp.z == 0.0f) perp = mk(0.0f, 0.0f, 1.0f);   // exact-zero test on the SUM (:656)
     else perp = vnormalize(perp);
     const V3 rp = vsub(relPos, vmuls(vnormalize(axis), focal));
-    pre[3 * o + 0] = make_float4(rp.x, rp.y, rp.z, sd);
-    pre[3 * o + 1] = make_float4(axis.x, axis.y, axis.z, focal);
-    pre[3 * o + 2] = make_float4(perp.x, perp.y, perp.z, kConeSigmas * fabsf(sd));
+    const V3 pxa = vcross(perp, axis);                  // the two sample-independent factors of the first rotation
+    const float pda = vdot(perp, axis);
+    pre[kPreStride * o + 0] = make_float4(rp.x, rp.y, rp.z, sd);
+    pre[kPreStride * o + 1] = make_float4(axis.x, axis.y, axis.z, focal);
+    pre[kPreStride * o + 2] = make_float4(perp.x, perp.y, perp.z, kConeSigmas * fabsf(sd));
+    pre[kPreStride * o + 3] = make_float4(pxa.x, pxa.y, pxa.z, pda);
 }
 
-__device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const DevicePose& P, Rng& rng,
-                                             float& splayOut)
+__device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const float4 p3, const DevicePose& P,
+                                             Rng& rng, float& splayOut)
 {
     const V3 rp = mk(p0.x, p0.y, p0.z);
     const V3 axis = mk(p1.x, p1.y, p1.z);
@@ -213,7 +217,10 @@ __device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, c
     const float splay = rngNormal(rng) * p0.w;
     splayOut = splay;
     const float axisAngle = rngUniform(rng) * crm::kPi;
-    const V3 splayed = rotatePoint(axis, splay, perp);
+    // = rotatePoint(axis, splay, perp) with cross(perp, axis) and dot(perp, axis) taken from the table
+    float sSn, sCs;
+    crm::sincos(splay, sSn, sCs);
+    const V3 splayed = vadd(vadd(vmuls(axis, sCs), vmuls(mk(p3.x, p3.y, p3.z), sSn)), vmuls(perp, (1.0f - sCs) * p3.w));
     const V3 rd = rotatePoint(splayed, axisAngle, axis);
     const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
     Ray r;
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     const int f = live ? (int)(idx / ep.N) : 0, o = live ? (int)(idx - (long long)f * ep.N) : 0;
     DevicePose P = ep.pose;
     if (ep.poses) P = ep.poses[f];
-    const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
+    const float4 p0 = __ldg(ep.pre + kPreStride * o), p1 = __ldg(ep.pre + kPreStride * o + 1), p2 = __ldg(ep.pre + kPreStride * o + 2);
     const V3 rp = mk(p0.x, p0.y, p0.z), a = mk(p1.x, p1.y, p1.z);
     const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
     const float half = p2.w * 1.01f + 1.0e-3f;
@@ -657,9 +664,10 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 pose.xy = b.x; pose.xz = b.y; pose.yx = b.z; pose.yy = b.w;
                 pose.yz = c.x; pose.zx = c.y; pose.zy = c.z; pose.zz = c.w;
             }
-            const float4 p0 = __ldg(ep.pre + 3 * o), p1 = __ldg(ep.pre + 3 * o + 1), p2 = __ldg(ep.pre + 3 * o + 2);
+            const float4* pp4 = ep.pre + kPreStride * (size_t)o;
+            const float4 p0 = __ldg(pp4), p1 = __ldg(pp4 + 1), p2 = __ldg(pp4 + 2), p3 = __ldg(pp4 + 3);
             float splay;
-            const Ray ray = ommatidialRay(p0, p1, p2, pose, rng, splay);
+            const Ray ray = ommatidialRay(p0, p1, p2, p3, pose, rng, splay);
             int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
             if (ep.entries != nullptr && fabsf(splay) <= p2.w) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
             if (MULTI) {   // park the state in shared memory: its 8 registers are dead while the ray is traced

@@ -353,7 +353,7 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
     if (cs.ommDirty || !cs.dOmm) {
         dfree(cs.dOmm); dfree(cs.dPre);
         cs.dOmm = dallocT<float4>(2 * static_cast<size_t>(N));
-        cs.dPre = dallocT<float4>(3 * static_cast<size_t>(N));
+        cs.dPre = dallocT<float4>(kPreStride * static_cast<size_t>(N));
         CR_CUDA(cudaMemcpyAsync(cs.dOmm, cam.ommatidia.data(), sizeof(Ommatidium) * static_cast<size_t>(N), cudaMemcpyHostToDevice, stream_));
         launchPrepOmmatidia(cs.dOmm, N, cs.dPre, stream_);
         launches_++;
