@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "cr_device.h"
 #include "cr_math.h"
@@ -765,6 +766,84 @@ __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restr
     }
 }
 
+// K1b, TMA form (used when S % 4 == 0, i.e. when every row segment is 16-byte aligned): one warp per kSumRows rows.
+// Lane 0 is the producer: per tile it arms the stage's mbarrier with the expected byte count and issues one
+// bulk asynchronous copy (cp.async.bulk, the 1-D TMA path: no per-thread addresses, no registers) per row segment
+// of kSumChunk samples = 1536 contiguous bytes.  The copies complete on the mbarrier; the warp waits on its phase
+// bit and lanes 0 .. 3*rows-1 walk their (row, channel) chains through the landed tile while the next two tiles
+// are in flight.  Row stride = 4 mod 32 floats: 16-byte aligned for the bulk copy and conflict-free for the walk.
+constexpr int kTmaStride = 3 * kSumChunk + 4;
+
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarArriveExpectTx(uint64_t* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(smemDst)), "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nCR_MBAR_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CR_MBAR_DONE;\nbra CR_MBAR_WAIT;\nCR_MBAR_DONE:\n}"
+                 ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
+                                                      uchar4* __restrict__ fastRow, int fastRowCount)
+{
+    __shared__ __align__(128) float tile[kSumStages][kSumRows * kTmaStride];
+    __shared__ __align__(8) uint64_t full[kSumStages];
+    const int row0 = blockIdx.x * kSumRows;
+    const int rows = min(kSumRows, NF - row0);
+    const int lane = threadIdx.x;
+    const size_t rowFloats = 3 * (size_t)S;
+    const float* base = samples + rowFloats * (size_t)row0;
+    const int nChunks = (S + kSumChunk - 1) / kSumChunk;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kSumStages; st++) mbarInit(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int c) {
+        if (c < nChunks && lane == 0) {
+            const unsigned bytes = 12u * (unsigned)min(kSumChunk, S - c * kSumChunk);     // S % 4 == 0: a multiple of 16
+            uint64_t* bar = &full[c % kSumStages];
+            float* dst = tile[c % kSumStages];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // earlier generic reads of this stage are done
+            mbarArriveExpectTx(bar, bytes * (unsigned)rows);
+            for (int r = 0; r < rows; r++) bulkLoad(dst + r * kTmaStride, base + rowFloats * r + 3 * (size_t)c * kSumChunk, bytes, bar);
+        }
+    };
+    issue(0);
+    issue(1);
+    const int myRow = lane / 3, ch = lane - 3 * myRow;
+    const bool summing = myRow < rows;
+    float sum = 0.0f;
+    for (int c = 0; c < nChunks; c++) {
+        mbarWait(&full[c % kSumStages], (unsigned)((c / kSumStages) & 1));
+        issue(c + 2);                                   // reuses the stage of tile c-1 (all lanes left it at the __syncwarp below)
+        if (summing) {
+            const float* q = &tile[c % kSumStages][myRow * kTmaStride + ch];
+            const int ns = min(kSumChunk, S - c * kSumChunk);
+            if (ns == kSumChunk) {
+#pragma unroll 16
+                for (int k = 0; k < kSumChunk; k++) sum += q[3 * k];
+            } else {
+                for (int k = 0; k < ns; k++) sum += q[3 * k];
+            }
+        }
+        __syncwarp();
+    }
+    if (summing) reinterpret_cast<float*>(summed + row0 + myRow)[ch] = sum;
+    if (fastRow != nullptr) {
+        const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor(sum, g, b);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2: vector projections (shaders.cu:375-406) and raw samples (shaders.cu:354-369)
 // ------------------------------------------------------------------------------------------
@@ -981,8 +1060,12 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     else if (eye.poses) k_traceCompound<false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     const long long nf = (long long)eye.N * eye.nFrames;
-    k_sumSamples<<<(unsigned)((nf + kSumRows - 1) / kSumRows), kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow,
-                                                                                         eye.fastRowCount);
+    static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();
+    const unsigned sumGrid = (unsigned)((nf + kSumRows - 1) / kSumRows);
+    if (useTma && eye.S % 4 == 0)
+        k_sumSamplesTma<<<sumGrid, 32, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+    else
+        k_sumSamples<<<sumGrid, kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
 }
 
 void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream)

@@ -18,7 +18,7 @@ for scene, cam in (("data/test-scene/test-scene.gltf", b"insect-cam-2"), ("data/
     N = lib.getCurrentEyeOmmatidialCount()
     for frontier in (0, 1):
         lib.crDebugSetEntryFrontier(frontier, 2, 0)
-        for S in (1, 5, 33, 130):                                   # partial warps, partial K1b tiles
+        for S in (1, 4, 5, 33, 64, 130, 132):                       # partial warps, partial K1b tiles, TMA (S % 4 == 0) and cp.async forms
             lib.setCurrentEyeSamplesPerOmmatidium(S)
             for shader, size in ((b"spherical_orientationwise", (64, 48)), (b"single_dimension_fast", (N, 1)), (b"raw_ommatidial_samples", (N, S)),
                                  (b"single_dimension", (77, 3)), (b"spherical_positionwise_ids", (40, 30))):
