@@ -769,10 +769,14 @@ __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restr
 // K1b, TMA form (used when S % 4 == 0, i.e. when every row segment is 16-byte aligned): one warp per kSumRows rows.
 // Lane 0 is the producer: per tile it arms the stage's mbarrier with the expected byte count and issues one
 // bulk asynchronous copy (cp.async.bulk, the 1-D TMA path: no per-thread addresses, no registers) per row segment
-// of kSumChunk samples = 1536 contiguous bytes.  The copies complete on the mbarrier; the warp waits on its phase
+// of kTmaChunk samples = 768 contiguous bytes.  The copies complete on the mbarrier; the warp waits on its phase
 // bit and lanes 0 .. 3*rows-1 walk their (row, channel) chains through the landed tile while the next two tiles
 // are in flight.  Row stride = 4 mod 32 floats: 16-byte aligned for the bulk copy and conflict-free for the walk.
-constexpr int kTmaStride = 3 * kSumChunk + 4;
+#ifndef CR_TMA_CHUNK
+#define CR_TMA_CHUNK 64
+#endif
+constexpr int kTmaChunk = CR_TMA_CHUNK;          // samples per row segment: 64 -> 18.6 KB per CTA, the whole 10k-ommatidia frame is one wave
+constexpr int kTmaStride = 3 * kTmaChunk + 4;
 
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
@@ -800,7 +804,7 @@ __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ 
     const int lane = threadIdx.x;
     const size_t rowFloats = 3 * (size_t)S;
     const float* base = samples + rowFloats * (size_t)row0;
-    const int nChunks = (S + kSumChunk - 1) / kSumChunk;
+    const int nChunks = (S + kTmaChunk - 1) / kTmaChunk;
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < kSumStages; st++) mbarInit(&full[st], 1);
@@ -809,12 +813,12 @@ __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ 
     __syncwarp();
     auto issue = [&](int c) {
         if (c < nChunks && lane == 0) {
-            const unsigned bytes = 12u * (unsigned)min(kSumChunk, S - c * kSumChunk);     // S % 4 == 0: a multiple of 16
+            const unsigned bytes = 12u * (unsigned)min(kTmaChunk, S - c * kTmaChunk);     // S % 4 == 0: a multiple of 16
             uint64_t* bar = &full[c % kSumStages];
             float* dst = tile[c % kSumStages];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // earlier generic reads of this stage are done
             mbarArriveExpectTx(bar, bytes * (unsigned)rows);
-            for (int r = 0; r < rows; r++) bulkLoad(dst + r * kTmaStride, base + rowFloats * r + 3 * (size_t)c * kSumChunk, bytes, bar);
+            for (int r = 0; r < rows; r++) bulkLoad(dst + r * kTmaStride, base + rowFloats * r + 3 * (size_t)c * kTmaChunk, bytes, bar);
         }
     };
     issue(0);
@@ -827,10 +831,10 @@ __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ 
         issue(c + 2);                                   // reuses the stage of tile c-1 (all lanes left it at the __syncwarp below)
         if (summing) {
             const float* q = &tile[c % kSumStages][myRow * kTmaStride + ch];
-            const int ns = min(kSumChunk, S - c * kSumChunk);
-            if (ns == kSumChunk) {
+            const int ns = min(kTmaChunk, S - c * kTmaChunk);
+            if (ns == kTmaChunk) {
 #pragma unroll 16
-                for (int k = 0; k < kSumChunk; k++) sum += q[3 * k];
+                for (int k = 0; k < kTmaChunk; k++) sum += q[3 * k];
             } else {
                 for (int k = 0; k < ns; k++) sum += q[3 * k];
             }
