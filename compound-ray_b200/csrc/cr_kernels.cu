@@ -10,7 +10,8 @@
 // K0b k_buildEntries       per (frame, ommatidium): BVH subtree roots its sample cone can reach (entry frontier)
 // K1  k_traceCompound      raygen + BVH traversal + shading, one sample ray per lane
 //                          (shaders.cu:664-731 + 110-137 + 740-811)
-// K1b k_sumSamples         exact-order per-ommatidium sum (shaders.cu:341-347) + 8-bit row of single_dimension_fast
+// K1b k_sumSamples[Tma]    exact-order per-ommatidium sum (shaders.cu:341-347) + 8-bit row of single_dimension_fast;
+//                          TMA bulk copies + mbarrier when S % 4 == 0, cp.async otherwise
 // K2  k_projectVector/Raw  single_dimension[_fast], raw_ommatidial_samples (shaders.cu:354-406)
 // K3  k_buildProjectionMap nearest-ommatidium map of the spherical modes, cached per eye/size
 //     k_projectMap         map lookup + make_color, or ids                (shaders.cu:412-640)
@@ -703,6 +704,8 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
 
 // K1b: summed[f][o].ch = ((0 + c[f][o][0]) + c[f][o][1]) + ... + c[f][o][S-1]: the reference's sequential
 // fp32 order (shaders.cu:341-347), so each (row, channel) is one dependent chain of S additions.
+// Two forms: the TMA kernel below (k_sumSamplesTma, bulk copies + mbarrier) whenever S % 4 == 0, and this
+// cp.async form for every other S (row segments that are not 16-byte aligned).
 // A CTA owns kSumRows consecutive (frame, ommatidium) rows.  Its 96 threads stream tiles of
 // kSumChunk samples per row into shared memory with cp.async -- coalesced 384-byte pieces of the
 // 12*S contiguous bytes of a row ([row][s][3] layout), two tiles in flight, no registers held --
