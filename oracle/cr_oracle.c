@@ -10,10 +10,18 @@
  *     tests/golden/xorwow_kat.json).
  *   - Loader math (node transforms, camera axes): pinned against the reference's sutil headers
  *     compiled from /root/reference (oracle/_ref/sutil_kat, golden vectors in tests/golden/).
- *   - Traversal / hit selection: "parity unpinned" -- the reference delegates it to the closed
- *     NVIDIA OptiX driver (shaders.cu:110-137), ships no tests or golden images
- *      and cannot be built here (no OptiX SDK).  The oracle restates the
- *     documented semantics (closest hit, two-sided, tmin/tmax) with Moller-Trumbore.
+ *   - Whole frames: pinned against six frames the reference itself rendered and its authors
+ *     committed beside their scripts (python-examples/{alias-demonstration,heterogeneous-demonstration,
+ *     overview-images}; tests/golden/reference_outputs.tar.gz, tests/test_reference_outputs.py): every
+ *     ommatidium that sees only sky -- 1131 of them over the six frames -- is reproduced byte for byte.
+ *     That covers .eye parsing, camera pose, RNG stream layout and draw order, the sample cone, the
+ *     world transform, simple_sky, the sample average, the spherical projection, make_color and the
+ *     PPM orientation.  The ground of those frames is the authors' unpublished natural environment
+ *     and cannot be compared.
+ *   - Traversal / hit selection and textured shading: "parity unpinned" -- the reference delegates
+ *     the closest hit to the closed NVIDIA OptiX driver (shaders.cu:110-137), no stored frame shows
+ *     geometry that is in the checkout, and the reference cannot be built here (no OptiX SDK).  The
+ *     oracle restates the documented semantics (closest hit, two-sided, tmin/tmax) with Moller-Trumbore.
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  * Floating point: plain IEEE binary32, one rounding per written operation (compile with

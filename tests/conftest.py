@@ -35,6 +35,20 @@ def ref_data():
 
 
 @pytest.fixture(scope="session")
+def ref_outputs():
+    """Directory holding frames the reference itself rendered (tests/golden/reference_outputs.tar.gz)."""
+    out = os.path.join(DATA_DIR, "reference-outputs")
+    stamp = os.path.join(out, ".unpacked")
+    arc = os.path.join(ROOT, "tests", "golden", "reference_outputs.tar.gz")
+    if not os.path.exists(stamp) or os.path.getmtime(stamp) < os.path.getmtime(arc):
+        os.makedirs(out, exist_ok=True)
+        with tarfile.open(arc) as tar:
+            tar.extractall(out, filter="data")
+        open(stamp, "w").close()
+    return out
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O
     O.lib()

@@ -10,6 +10,13 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
   stb_jpeg_kat.{json,npz} those streams decoded by the reference's vendored stb_image.h (oracle/_ref/stb_kat)
   png/*.png              small PNG streams of every colour type / bit depth / tRNS form, plain and Adam7 (own writer)
   stb_png_kat.{json,npz}  those streams decoded by the reference's vendored stb_image.h
+  reference_outputs.tar.gz  OUTPUT frames the reference itself rendered and its authors committed next to the
+                         scripts that made them (python-examples/alias-demonstration/viewpoint-experiment.py,
+                         heterogeneous-demonstration/demonstration.py, overview-images/overviewImages.py), plus the
+                         two .eye tables those scripts read.  They were rendered in the authors' (unpublished)
+                         natural environment, of which data/natural-standin-sky.gltf keeps the camera, the eye and
+                         the simple_sky background: every ommatidium that sees only sky is a known answer
+                         (tests/test_reference_outputs.py).
 """
 import os
 import subprocess
@@ -32,6 +39,32 @@ FILES = {
     "sim-environment/env_2.gltf": TOY + "/env_2.gltf",
     "sim-environment/eyes/AM_60185-real.eye": TOY + "/eyes/AM_60185-real.eye",
 }
+
+
+PY = "python-examples"
+OUTPUTS = {
+    # archive name                                   : path under /root/reference
+    "alias-demonstration/spherical-image-0-samples.ppm": PY + "/alias-demonstration/output/view-images/spherical-image-0-samples.ppm",
+    "alias-demonstration/spherical-image-700-samples.ppm": PY + "/alias-demonstration/output/view-images/spherical-image-700-samples.ppm",
+    "heterogeneous-demonstration/1000-extreme-horizontallyAcute-variableDegree.eye":
+        PY + "/heterogeneous-demonstration/1000-extreme-horizontallyAcute-variableDegree.eye",
+    "heterogeneous-demonstration/heterogeneous-omms-4.ppm": PY + "/heterogeneous-demonstration/heterogeneous-omms-4.ppm",
+    "heterogeneous-demonstration/homogeneous-omms-small-4.ppm": PY + "/heterogeneous-demonstration/homogeneous-omms-small-4.ppm",
+    "overview-images/uniform-omms.ppm": PY + "/overview-images/uniform-omms.ppm",
+    "overview-images/acute-omms.ppm": PY + "/overview-images/acute-omms.ppm",
+}
+
+
+def pack(out, files):
+    with tarfile.open(out, "w:gz", compresslevel=9) as tar:
+        for arc, src in sorted(files.items()):
+            info = tar.gettarinfo(os.path.join(REF, src), arcname=arc)
+            info.mtime = 0
+            info.uid = info.gid = 0
+            info.uname = info.gname = ""
+            with open(os.path.join(REF, src), "rb") as fh:
+                tar.addfile(info, fh)
+    print(out, os.path.getsize(out), "bytes")
 
 
 def make_jpeg_kat():
@@ -211,16 +244,8 @@ def main():
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sutil_kat")], stdout=f)
     make_jpeg_kat()
     make_png_kat()
-    out = os.path.join(HERE, "reference_data.tar.gz")
-    with tarfile.open(out, "w:gz", compresslevel=9) as tar:
-        for arc, src in sorted(FILES.items()):
-            info = tar.gettarinfo(os.path.join(REF, src), arcname=arc)
-            info.mtime = 0
-            info.uid = info.gid = 0
-            info.uname = info.gname = ""
-            with open(os.path.join(REF, src), "rb") as fh:
-                tar.addfile(info, fh)
-    print(out, os.path.getsize(out), "bytes")
+    pack(os.path.join(HERE, "reference_data.tar.gz"), FILES)
+    pack(os.path.join(HERE, "reference_outputs.tar.gz"), OUTPUTS)
 
 
 if __name__ == "__main__":
