@@ -52,6 +52,12 @@ OUTPUTS = {
     "heterogeneous-demonstration/homogeneous-omms-small-4.ppm": PY + "/heterogeneous-demonstration/homogeneous-omms-small-4.ppm",
     "overview-images/uniform-omms.ppm": PY + "/overview-images/uniform-omms.ppm",
     "overview-images/acute-omms.ppm": PY + "/overview-images/acute-omms.ppm",
+    # quantified-experiment.py: per-ommatidium variance of the 8-bit eye vector over 1000 / 100 consecutive frames;
+    # the number in the name is the loop index, i.e. samples per ommatidium minus one
+    "alias-demonstration/vector-data/variance-0-samples.txt": PY + "/alias-demonstration/output/vector-data/variance-0-samples.txt",
+    "alias-demonstration/vector-data-100samples/variance-0-samples.txt": PY + "/alias-demonstration/output/vector-data-100samples/variance-0-samples.txt",
+    "alias-demonstration/vector-data-100samples/variance-3-samples.txt": PY + "/alias-demonstration/output/vector-data-100samples/variance-3-samples.txt",
+    "alias-demonstration/vector-data-100samples/variance-15-samples.txt": PY + "/alias-demonstration/output/vector-data-100samples/variance-15-samples.txt",
 }
 
 

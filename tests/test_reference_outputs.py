@@ -5,6 +5,8 @@ that made them:
   python-examples/alias-demonstration/viewpoint-experiment.py:27-66   -> output/view-images/spherical-image-{0,700}-samples.ppm
   python-examples/heterogeneous-demonstration/demonstration.py:60-125 -> heterogeneous-omms-4.ppm, homogeneous-omms-small-4.ppm
   python-examples/overview-images/overviewImages.py:88-131            -> uniform-omms.ppm, acute-omms.ppm
+  python-examples/alias-demonstration/quantified-experiment.py:76-137 -> output/vector-data{,-100samples}/variance-*-samples.txt
+    (per-ommatidium variance of the 8-bit single_dimension_fast vector over 1000 / 100 CONSECUTIVE frames)
 All of them look through `insect-eye-spherical-projector` with `simple_sky`.  They were rendered in the
 authors' natural environment, which is not published (python-examples/readme.txt:4): the checkout holds
 data/natural-standin-sky.gltf instead -- same camera node, same eye, same background shader, another ground.
@@ -172,7 +174,88 @@ def test_the_stored_frames_discriminate(oracle, loader, er, ref_data, ref_output
     assert cells > 150 and exact < 0.2 * cells, (cells, exact)
 
 
+# ------------------------------------------------------------------------------------------ variance over many frames
+# quantified-experiment.py:76-137.  The script looks through `insect-eye-fast-vector`, a camera of the same node
+# pose and eye whose compound-structure path no longer resolves in the checkout (it lacks the "eyes/" prefix, so
+# the camera is skipped at load: MulticamScene.cpp:266-279); the same eye under single_dimension_fast is
+# `insect-eye-spherical-projector` with its shader name switched.
+# stored file -> (samples per ommatidium, frames): the number in the name is the loop index = S - 1
+VARIANCE_RUNS = {
+    "alias-demonstration/vector-data/variance-0-samples.txt": (1, 1000),
+    "alias-demonstration/vector-data-100samples/variance-0-samples.txt": (1, 100),
+    "alias-demonstration/vector-data-100samples/variance-3-samples.txt": (4, 100),
+    "alias-demonstration/vector-data-100samples/variance-15-samples.txt": (16, 100),
+}
+
+
+def script_variance(frames):
+    """quantified-experiment.py:110-121: sum over frames of |rgb - mean rgb|^2, divided by (frames - 1)."""
+    f = frames.astype(np.float64)
+    return (np.linalg.norm(f - f.mean(axis=0), axis=2) ** 2).sum(axis=0) / (len(f) - 1)
+
+
+def hold_to_stored_variance(var, clear, stored_path):
+    """A byte of one frame off by one moves a variance by ~|2d+1|/(F-1); the reference runs fast-math, so allow
+    that for a few ommatidia -- every other clear-sky ommatidium must have the stored variance itself, which
+    means each of its F frames had the reference's bytes."""
+    ref = np.loadtxt(stored_path)
+    assert ref.shape == var.shape
+    a, b = var[clear], ref[clear]
+    same = np.abs(a - b) <= 1e-9 * np.maximum(1.0, b)
+    assert clear.sum() >= 120, clear.sum()
+    assert same.mean() >= 0.97, (os.path.basename(stored_path), int(same.sum()), int(clear.sum()))
+    assert np.abs(a - b).max() <= 0.05, np.abs(a - b).max()
+    assert b.max() > 1.0                                                   # the sky does vary over a cone
+
+
+def oracle_vector_run(oracle, loader, ref_data, S, F):
+    """Frames 1..F after the sample count was set (frame 0 is the script's "ensure randoms are configured" call)."""
+    _, sh, cam = load_oracle_scene(loader, oracle, os.path.join(ref_data, SCENE), CAMERA)
+    omm = np.asarray(cam.ommatidia, dtype=np.float32).reshape(-1, 8)
+    N = len(omm)
+    eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(cam), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    eye.render_frame()
+    frames = np.zeros((F, N, 3), np.uint8)
+    clear = np.ones(N, bool)
+    for i in range(F):
+        frames[i] = eye.render_frame()[0, :, :3]
+        d = eye.last["dirs"].astype(np.float64)
+        lowest = (d[:, 1] / np.linalg.norm(d, axis=1)).reshape(S, N).min(axis=0)
+        clear &= (eye.last["hits"]["prim"].reshape(S, N) < 0).all(axis=0) & (lowest > TREE_LINE)
+    return frames, clear
+
+
+@pytest.mark.parametrize("stored", list(VARIANCE_RUNS))
+def test_oracle_reproduces_the_reference_variances(oracle, loader, ref_data, ref_outputs, stored):
+    S, F = VARIANCE_RUNS[stored]
+    frames, clear = oracle_vector_run(oracle, loader, ref_data, S, F)
+    hold_to_stored_variance(script_variance(frames), clear, os.path.join(ref_outputs, stored))
+
+
 # ------------------------------------------------------------------------------------------ product (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("stored", list(VARIANCE_RUNS))
+def test_product_reproduces_the_reference_variances(lib, er, oracle, loader, ref_data, ref_outputs, stored):
+    """quantified-experiment.py:76-99 through the C ABI: F consecutive renderFrame + getFramePointer calls."""
+    S, F = VARIANCE_RUNS[stored]
+    oframes, clear = oracle_vector_run(oracle, loader, ref_data, S, F)
+    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
+    assert lib.gotoCameraByName(CAMERA.encode())
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N = lib.getCurrentEyeOmmatidialCount()
+    er.setRenderSize(lib, N, 1)                                            # quantified-experiment.py:77
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    lib.renderFrame()                                                      # "first call to ensure randoms are configured"
+    frames = np.zeros((F, N, 3), np.uint8)
+    for i in range(F):
+        lib.renderFrame()
+        frames[i] = lib.getFramePointer()[0, :, :3]
+    assert np.array_equal(frames[:, clear], oframes[:, clear]), "product and oracle agree on every frame of the sky-only ommatidia"
+    hold_to_stored_variance(script_variance(frames), clear, os.path.join(ref_outputs, stored))
+
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scenario", list(SCENARIOS))
 def test_product_reproduces_the_reference_frames(lib, er, oracle, loader, ref_data, ref_outputs, tmp_path, scenario):
