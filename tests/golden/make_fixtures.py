@@ -16,7 +16,8 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
                          two .eye tables those scripts read.  They were rendered in the authors' (unpublished)
                          natural environment, of which data/natural-standin-sky.gltf keeps the camera, the eye and
                          the simple_sky background: every ommatidium that sees only sky is a known answer
-                         (tests/test_reference_outputs.py).
+                         (tests/test_reference_outputs.py).  Also docs/images/standin-sky-render.png, a screenshot
+                         of the reference's viewer on the stand-in scene itself (ground texture and terrain included).
 """
 import os
 import subprocess
@@ -52,6 +53,8 @@ OUTPUTS = {
     "heterogeneous-demonstration/homogeneous-omms-small-4.ppm": PY + "/heterogeneous-demonstration/homogeneous-omms-small-4.ppm",
     "overview-images/uniform-omms.ppm": PY + "/overview-images/uniform-omms.ppm",
     "overview-images/acute-omms.ppm": PY + "/overview-images/acute-omms.ppm",
+    # screenshot of the reference's GUI showing data/natural-standin-sky.gltf through its first camera (README figure)
+    "docs/images/standin-sky-render.png": "docs/images/standin-sky-render.png",
     # quantified-experiment.py: per-ommatidium variance of the 8-bit eye vector over 1000 / 100 consecutive frames;
     # the number in the name is the loop index, i.e. samples per ommatidium minus one
     "alias-demonstration/vector-data/variance-0-samples.txt": PY + "/alias-demonstration/output/vector-data/variance-0-samples.txt",
