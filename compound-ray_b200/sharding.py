@@ -45,6 +45,58 @@ def unpad(gathered, world: int, n_poses: int):
     return torch.cat(parts, dim=0)
 
 
+class ChunkedPoseGather:
+    """The allgather of a pose-sharded run, issued in chunks while the run is still rendering.
+
+    Every rank renders its pose block chunk by chunk (crRenderPoseBatch writes the rows of chunk c straight into
+    `send_rows(c)`, a slice of this rank's send block) and calls `issue(c)` after each: one asynchronous allgather
+    per chunk, on the process group's own stream, whose output views ARE the final [rank][row] places -- no staging
+    and no reshuffle.  The collective of chunk c runs while chunk c+1 is traced; `finish()` waits for all of them and
+    returns the rows in pose order.  Chunks are cut on the PADDED block, so every rank issues the same collectives
+    whatever its share of the poses.  Consecutive crRenderPoseBatch calls continue the sample streams, so chunking
+    does not change a byte of the result."""
+
+    def __init__(self, rank: int, world: int, n_poses: int, row_shape, dtype, device, chunk: int, dist=None):
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        self.rank, self.world, self.n_poses, self.dist = rank, world, n_poses, dist
+        self.blk = padded_block_size(world, n_poses)
+        self.lo, self.hi = pose_block(rank, world, n_poses)
+        row_shape = tuple(row_shape)
+        self.send = torch.zeros((self.blk,) + row_shape, dtype=dtype, device=device)
+        self.gathered = torch.zeros((world, self.blk) + row_shape, dtype=dtype, device=device)
+        chunk = max(1, int(chunk))
+        self.chunks = [(c0, min(c0 + chunk, self.blk)) for c0 in range(0, self.blk, chunk)]
+        self.handles = []
+
+    def local_poses(self, c: int) -> tuple[int, int]:
+        """Local pose indices [a, b) of this rank that fall into chunk c (empty for pure padding)."""
+        c0, c1 = self.chunks[c]
+        n = self.hi - self.lo
+        return min(c0, n), min(c1, n)
+
+    def send_rows(self, c: int):
+        """Slice of the send block that receives the rows of chunk c."""
+        c0, c1 = self.chunks[c]
+        return self.send[c0:c1]
+
+    def issue(self, c: int):
+        c0, c1 = self.chunks[c]
+        if self.world == 1:
+            self.gathered[0, c0:c1] = self.send[c0:c1]
+            return
+        outs = [self.gathered[r, c0:c1] for r in range(self.world)]          # contiguous views of the final buffer
+        self.handles.append(self.dist.all_gather(outs, self.send[c0:c1], async_op=True))
+
+    def finish(self):
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        flat = self.gathered.view((self.world * self.blk,) + tuple(self.gathered.shape[2:]))
+        return unpad(flat, self.world, self.n_poses)
+
+
 # ---------------------------------------------------------------------------------------------
 # Secondary partition: one pose, large N*S -- rank r owns the ommatidium rows [lo, hi) of the eye.
 # Stream ids keep the GLOBAL indices (crSetOmmatidialShard), so the gathered per-ommatidium RGB

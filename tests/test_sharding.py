@@ -52,6 +52,18 @@ def _worker(rank, world, port, out_dir, data_dir):
     dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
     result = sharding.unpad(gathered.numpy(), world, P)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), result)
+    # the same run with the gather issued in chunks of 2 poses while the next chunk renders
+    eye.set_first_frame(lo)
+    cg = sharding.ChunkedPoseGather(rank, world, P, (N, 4), torch.uint8, "cpu", 2, dist)
+    assert cg.chunks == [(0, 2), (2, 4)] and cg.blk == blk
+    for c in range(len(cg.chunks)):
+        a, b = cg.local_poses(c)
+        rows = cg.send_rows(c)
+        for i in range(a, b):
+            eye.pose = O.make_pose(positions[lo + i], cam.x_axis, cam.y_axis, cam.z_axis)
+            rows[i - cg.chunks[c][0]] = torch.from_numpy(eye.render_frame(method="brute")[0].copy())
+        cg.issue(c)
+    np.save(os.path.join(out_dir, f"chunked_rank{rank}.npy"), cg.finish().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,6 +74,8 @@ def test_sharded_run_equals_sequential_run(ref_data, oracle, loader, tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path), ref_data), nprocs=world, join=True)
     r0 = np.load(tmp_path / "rank0.npy"); r1 = np.load(tmp_path / "rank1.npy")
     assert np.array_equal(r0, r1), "every rank holds the full result"
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"chunked_rank{r}.npy"), r0), "chunked, overlapped gather = single gather"
     # sequential reference: one process, frames 0..P-1
     path = os.path.join(ref_data, "data", "test-scene", "test-scene.gltf")
     sc = loader.load_scene(path)
