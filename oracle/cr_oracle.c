@@ -20,7 +20,9 @@
  *     and cannot be compared.
  *   - Closest hit + textured shading: pinned against a screenshot of the reference's viewer on
  *     data/natural-standin-sky.gltf (docs/images/standin-sky-render.png): 99.99 % of 160 000 pixels
- *     within one 8-bit step, 94.8 % exact (the reference runs fast-math).
+ *     within one 8-bit step, 94.8 % exact (the reference runs fast-math); and against a screenshot of
+ *     data/test-scene/test-scene.gltf through insect-cam-1 (docs/images/test-scene-running.png,
+ *     S = 41, frame 8248): all 1000 ommatidia byte-exact.
  *   - "Parity unpinned" remains for tie-breaking between coincident hits: the reference delegates
  *     the closest hit to the closed NVIDIA OptiX driver (shaders.cu:110-137), no stored output
  *     exercises ties, and the reference cannot be built here (no OptiX SDK).  The oracle restates the

@@ -55,6 +55,8 @@ OUTPUTS = {
     "overview-images/acute-omms.ppm": PY + "/overview-images/acute-omms.ppm",
     # screenshot of the reference's GUI showing data/natural-standin-sky.gltf through its first camera (README figure)
     "docs/images/standin-sky-render.png": "docs/images/standin-sky-render.png",
+    # ... and showing data/test-scene/test-scene.gltf through insect-cam-1 (found to be S = 41, frame 8248)
+    "docs/images/test-scene-running.png": "docs/images/test-scene-running.png",
     # quantified-experiment.py: per-ommatidium variance of the 8-bit eye vector over 1000 / 100 consecutive frames;
     # the number in the name is the loop index, i.e. samples per ommatidium minus one
     "alias-demonstration/vector-data/variance-0-samples.txt": PY + "/alias-demonstration/output/vector-data/variance-0-samples.txt",

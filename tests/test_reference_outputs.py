@@ -7,7 +7,8 @@ that made them:
   python-examples/overview-images/overviewImages.py:88-131            -> uniform-omms.ppm, acute-omms.ppm
   python-examples/alias-demonstration/quantified-experiment.py:76-137 -> output/vector-data{,-100samples}/variance-*-samples.txt
     (per-ommatidium variance of the 8-bit single_dimension_fast vector over 1000 / 100 CONSECUTIVE frames)
-  docs/images/standin-sky-render.png -- a screenshot of the reference's viewer on data/natural-standin-sky.gltf (see the end)
+  docs/images/standin-sky-render.png, docs/images/test-scene-running.png -- screenshots of the reference's viewer on
+    data/natural-standin-sky.gltf and data/test-scene/test-scene.gltf, scenes that ARE in the checkout (see the end)
 The first four look through `insect-eye-spherical-projector` with `simple_sky`.  They were rendered in the
 authors' natural environment, which is not published (python-examples/readme.txt:4): the checkout holds
 data/natural-standin-sky.gltf instead -- same camera node, same eye, same background shader, another ground.
@@ -245,11 +246,11 @@ SHOT = os.path.join("docs", "images", "standin-sky-render.png")
 SHOT_CONTENT = (slice(45, 445), slice(10, 410))                            # client area inside the window frame
 
 
-def viewer_screenshot(lib, ref_outputs):
+def viewer_screenshot(lib, ref_outputs, name=SHOT):
     """uint8[400][400][3], rows top-down; decoded by the product's PNG reader (byte-exact vs stb_image: test_host.py)."""
     import ctypes as C
     w, h = C.c_int(), C.c_int()
-    assert lib.crDebugDecodeImageFile(os.path.join(ref_outputs, SHOT).encode(), C.byref(w), C.byref(h))
+    assert lib.crDebugDecodeImageFile(os.path.join(ref_outputs, name).encode(), C.byref(w), C.byref(h))
     px = np.zeros((h.value, w.value, 4), np.uint8)
     lib.crDebugCopyDecodedImage(px.ctypes.data)
     assert (px[44, 10:410, :3] < 64).all() and (px[445, 10:410, :3] == 0).all()   # title bar above, border below
@@ -304,6 +305,79 @@ def test_product_reproduces_the_viewer_screenshot(lib, er, oracle, loader, ref_d
     # measured on a B200: 95.8 % exact (ground 91.9 %), 99.992 % within one step
     print(f"product vs reference screenshot: {(diff == 0).mean():.4f} exact, {(diff <= 1).mean():.5f} within one step; "
           f"ground {(diff[ground] == 0).mean():.4f} exact")
+
+
+# ------------------------------------------------------------------------------------------ viewer screenshot, test scene
+# docs/images/test-scene-running.png: the viewer on data/test-scene/test-scene.gltf looking through `insect-cam-1`
+# (two presses of N from camera 0; 1000 ommatidia of 2 rad acceptance, spherical_orientationwise, default_background,
+# vertex-coloured meshes) at 400x400.  Neither the sample count nor the frame number is recorded with the figure.
+# PAGE_UP adds 10 samples (newGuiEyeRenderer/gui.cpp:35-36) and every change restarts the streams, so the candidates
+# are S = 1, 11, 21, ... and a frame count since the last change.  A search (60 ommatidia, S in 1..41, 30 000 frames
+# each; best near-miss 18 % of the cells) found exactly one pair at which EVERY cell matches: S = 41, frame 8248.
+# There all 1000 ommatidia have the screenshot's colour byte for byte and 6 of 160 000 pixels differ (cell borders):
+# a known answer for the stream positions after 8 248 frames (3+1 draws per frame pair), wide-cone sample directions,
+# __miss__default_background (atan2/asin), closest hits on the vertex-coloured meshes (159 ommatidia see geometry),
+# the 41-sample average, the projection and make_color.
+SHOT_TEST_SCENE = os.path.join("docs", "images", "test-scene-running.png")
+SHOT_S, SHOT_FRAME = 41, 8248
+
+
+def oracle_test_scene(oracle, loader, ref_data, frame_index):
+    path = os.path.join(ref_data, "data", "test-scene", "test-scene.gltf")
+    _, sh, cam = load_oracle_scene(loader, oracle, path, "insect-cam-1")
+    omm = np.asarray(cam.ommatidia, dtype=np.float32).reshape(-1, 8)
+    eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(cam), cam.projection, samples=SHOT_S)
+    eye.set_render_size(400, 400)
+    eye.set_first_frame(frame_index)        # == frame_index sequential frames (test_oracle.py::test_position_streams_*)
+    frame = eye.render_frame(method="brute")[:, :, :3].copy()
+    sees_geometry = (eye.last["hits"]["prim"].reshape(SHOT_S, len(omm)) >= 0).any(axis=0)
+    return frame, oracle.projection_map(omm, cam.projection, 400, 400), sees_geometry
+
+
+def cells_equal(frame, shot, pm, n):
+    """Number of ommatidia whose modal screenshot colour equals the frame's."""
+    same = 0
+    for o in range(n):
+        m = pm == o
+        vals, cnt = np.unique(shot[m], axis=0, return_counts=True)
+        same += int(np.array_equal(vals[cnt.argmax()], frame[m][0]))
+    return same
+
+
+def test_oracle_reproduces_the_test_scene_screenshot(lib, oracle, loader, ref_data, ref_outputs):
+    shot = viewer_screenshot(lib, ref_outputs, SHOT_TEST_SCENE)[::-1]                 # bottom-up like the frame
+    frame, pm, sees_geometry = oracle_test_scene(oracle, loader, ref_data, SHOT_FRAME)
+    assert sees_geometry.sum() > 100
+    assert cells_equal(frame, shot, pm, 1000) == 1000
+    assert (frame != shot).any(axis=2).sum() <= 16                                    # measured: 6 border pixels
+    for other in (SHOT_FRAME - 1, SHOT_FRAME + 1):                                    # the neighbouring frames do not match
+        f2, _, _ = oracle_test_scene(oracle, loader, ref_data, other)
+        assert cells_equal(f2, shot, pm, 1000) < 300
+
+
+@pytest.mark.gpu
+def test_product_reproduces_the_test_scene_screenshot(lib, er, oracle, loader, ref_data, ref_outputs):
+    """The viewer's own sequence through the C ABI: load, N, N, PAGE_UP x4, then frames 0..8248 one renderFrame each."""
+    shot = viewer_screenshot(lib, ref_outputs, SHOT_TEST_SCENE)[::-1]
+    oframe, pm, _ = oracle_test_scene(oracle, loader, ref_data, SHOT_FRAME)
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    lib.nextCamera(); lib.nextCamera()                                                # gui.cpp:30-32
+    assert lib.getCurrentCameraName() == b"insect-cam-1"
+    er.setRenderSize(lib, 400, 400)
+    for _ in range(4):
+        lib.changeCurrentEyeSamplesPerOmmatidiumBy(10)                                # gui.cpp:35-36
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == SHOT_S
+    for _ in range(SHOT_FRAME + 1):
+        lib.renderFrame()
+    frame = er.getFrame(lib, 400, 400)[:, :, :3]
+    assert np.array_equal(frame, oframe), "product == oracle on the test scene, byte for byte"
+    assert cells_equal(frame, shot, pm, 1000) == 1000
+    assert (frame != shot).any(axis=2).sum() <= 16
+    lib.setCurrentEyeSamplesPerOmmatidium(SHOT_S)                                     # the same frame by jumping the streams
+    lib.crSetFirstFrame(SHOT_FRAME)
+    lib.renderFrame()
+    assert np.array_equal(er.getFrame(lib, 400, 400)[:, :, :3], frame), "crSetFirstFrame(k) == k sequential frames"
+    lib.crSetFirstFrame(0)
 
 
 # ------------------------------------------------------------------------------------------ product (GPU)
