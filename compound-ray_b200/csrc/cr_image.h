@@ -128,6 +128,7 @@ inline ImageRGBA8 decodePNG(const uint8_t* data, size_t size)
     }
     if (!haveHdr) throw std::runtime_error("PNG without IHDR");
     if (W == 0 || H == 0) throw std::runtime_error("empty PNG");
+    if (W > (1u << 24) || H > (1u << 24) || static_cast<uint64_t>(W) * H > (uint64_t(1) << 28)) throw std::runtime_error("PNG too large");
     if (interlace > 1) throw std::runtime_error("bad PNG interlace method");
     int channels = 0;
     switch (ctype) {
@@ -155,6 +156,9 @@ inline ImageRGBA8 decodePNG(const uint8_t* data, size_t size)
         if (interlace && (W <= static_cast<uint32_t>(ox[p]) || H <= static_cast<uint32_t>(oy[p]))) pw[p] = ph[p] = 0;
         if (pw[p] && ph[p]) need += ((static_cast<size_t>(pw[p]) * bitsPerPixel + 7) / 8 + 1) * ph[p];
     }
+    // deflate cannot expand by more than 1032:1, so a header that asks for more than the IDAT bytes can deliver is
+    // corrupt: refuse it before allocating for it
+    if (need / 1032 > idat.size() + 16) throw std::runtime_error("PNG data too short for the image size it declares");
     std::vector<uint8_t> raw(need);
     uLongf rawLen = static_cast<uLongf>(raw.size());
     int zr = uncompress(raw.data(), &rawLen, idat.data(), static_cast<uLong>(idat.size()));

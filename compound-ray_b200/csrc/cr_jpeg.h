@@ -48,7 +48,7 @@ struct Component {
 
 class Decoder {
 public:
-    Decoder(const uint8_t* data, size_t size) : p_(data), end_(data + size) {}
+    Decoder(const uint8_t* data, size_t size) : begin_(data), p_(data), end_(data + size) {}
 
     ImageRGBA8 decode()
     {
@@ -143,6 +143,7 @@ private:
         for (int l = 1; l <= 16; l++) {
             h.valptr[l] = k;
             h.mincode[l] = code;
+            if (code + counts[l] > (1 << l)) fail("bad Huffman code lengths");   // before any table write: keeps code < 2^l below
             for (int i = 0; i < counts[l]; i++, k++, code++) {
                 if (l <= 9) {
                     const int first = code << (9 - l);
@@ -164,6 +165,12 @@ private:
         W_ = be16();
         const int n = byte();
         if (H_ <= 0 || W_ <= 0) fail("bad image size");
+        // A corrupt header must not turn into a multi-gigabyte allocation: bound the frame, and require at least one
+        // byte of stream per 512 pixels (an MCU whose blocks are all "DC unchanged, end of block" still costs 2 bits
+        // per block; progressive refinement scans only add to that).
+        const size_t pixels = static_cast<size_t>(W_) * static_cast<size_t>(H_);
+        if (pixels > (size_t(1) << 28)) fail("image too large");
+        if (pixels / 512 > static_cast<size_t>(end_ - begin_)) fail("stream too short for the frame size it declares");
         if (n != 1 && n != 3 && n != 4) fail("bad component count");
         if (len != 8 + 3 * n) fail("bad SOF length");
         comps_.assign(static_cast<size_t>(n), Component());
@@ -472,33 +479,38 @@ private:
     // ---- IJG islow inverse DCT ------------------------------------------------------------------
     static inline int fix(double x) { return static_cast<int>(x * 4096 + 0.5); }
     static inline uint8_t clamp255(int x) { return static_cast<uint8_t>(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+    // Integer arithmetic of the inverse DCT wraps modulo 2^32: coefficients of a valid stream stay far below the
+    // range of int, and a corrupt stream (whose pixels are garbage anyway) must not reach undefined behaviour.
+    static inline int wadd(int a, int b) { return static_cast<int>(static_cast<uint32_t>(a) + static_cast<uint32_t>(b)); }
+    static inline int wsub(int a, int b) { return static_cast<int>(static_cast<uint32_t>(a) - static_cast<uint32_t>(b)); }
+    static inline int wmul(int a, int b) { return static_cast<int>(static_cast<uint32_t>(a) * static_cast<uint32_t>(b)); }
     struct Idct1D { int x0, x1, x2, x3, t0, t1, t2, t3; };
     static inline Idct1D idct1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7)
     {
         Idct1D r;
         int p2 = s2, p3 = s6;
-        int p1 = (p2 + p3) * fix(0.5411961f);
-        int t2 = p1 + p3 * fix(-1.847759065f);
-        int t3 = p1 + p2 * fix(0.765366865f);
+        int p1 = wmul(wadd(p2, p3), fix(0.5411961f));
+        int t2 = wadd(p1, wmul(p3, fix(-1.847759065f)));
+        int t3 = wadd(p1, wmul(p2, fix(0.765366865f)));
         p2 = s0; p3 = s4;
-        int t0 = (p2 + p3) * 4096;
-        int t1 = (p2 - p3) * 4096;
-        r.x0 = t0 + t3; r.x3 = t0 - t3; r.x1 = t1 + t2; r.x2 = t1 - t2;
+        int t0 = wmul(wadd(p2, p3), 4096);
+        int t1 = wmul(wsub(p2, p3), 4096);
+        r.x0 = wadd(t0, t3); r.x3 = wsub(t0, t3); r.x1 = wadd(t1, t2); r.x2 = wsub(t1, t2);
         t0 = s7; t1 = s5; t2 = s3; t3 = s1;
-        p3 = t0 + t2;
-        int p4 = t1 + t3;
-        p1 = t0 + t3;
-        p2 = t1 + t2;
-        const int p5 = (p3 + p4) * fix(1.175875602f);
-        t0 = t0 * fix(0.298631336f);
-        t1 = t1 * fix(2.053119869f);
-        t2 = t2 * fix(3.072711026f);
-        t3 = t3 * fix(1.501321110f);
-        p1 = p5 + p1 * fix(-0.899976223f);
-        p2 = p5 + p2 * fix(-2.562915447f);
-        p3 = p3 * fix(-1.961570560f);
-        p4 = p4 * fix(-0.390180644f);
-        r.t3 = t3 + p1 + p4; r.t2 = t2 + p2 + p3; r.t1 = t1 + p2 + p4; r.t0 = t0 + p1 + p3;
+        p3 = wadd(t0, t2);
+        int p4 = wadd(t1, t3);
+        p1 = wadd(t0, t3);
+        p2 = wadd(t1, t2);
+        const int p5 = wmul(wadd(p3, p4), fix(1.175875602f));
+        t0 = wmul(t0, fix(0.298631336f));
+        t1 = wmul(t1, fix(2.053119869f));
+        t2 = wmul(t2, fix(3.072711026f));
+        t3 = wmul(t3, fix(1.501321110f));
+        p1 = wadd(p5, wmul(p1, fix(-0.899976223f)));
+        p2 = wadd(p5, wmul(p2, fix(-2.562915447f)));
+        p3 = wmul(p3, fix(-1.961570560f));
+        p4 = wmul(p4, fix(-0.390180644f));
+        r.t3 = wadd(wadd(t3, p1), p4); r.t2 = wadd(wadd(t2, p2), p3); r.t1 = wadd(wadd(t1, p2), p4); r.t0 = wadd(wadd(t0, p1), p3);
         return r;
     }
     static void idct(const short* d, uint8_t* out, int stride)
@@ -512,11 +524,11 @@ private:
                 v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
             } else {
                 Idct1D r = idct1d(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
-                r.x0 += 512; r.x1 += 512; r.x2 += 512; r.x3 += 512;
-                v[0] = (r.x0 + r.t3) >> 10; v[56] = (r.x0 - r.t3) >> 10;
-                v[8] = (r.x1 + r.t2) >> 10; v[48] = (r.x1 - r.t2) >> 10;
-                v[16] = (r.x2 + r.t1) >> 10; v[40] = (r.x2 - r.t1) >> 10;
-                v[24] = (r.x3 + r.t0) >> 10; v[32] = (r.x3 - r.t0) >> 10;
+                r.x0 = wadd(r.x0, 512); r.x1 = wadd(r.x1, 512); r.x2 = wadd(r.x2, 512); r.x3 = wadd(r.x3, 512);
+                v[0] = wadd(r.x0, r.t3) >> 10; v[56] = wsub(r.x0, r.t3) >> 10;
+                v[8] = wadd(r.x1, r.t2) >> 10; v[48] = wsub(r.x1, r.t2) >> 10;
+                v[16] = wadd(r.x2, r.t1) >> 10; v[40] = wsub(r.x2, r.t1) >> 10;
+                v[24] = wadd(r.x3, r.t0) >> 10; v[32] = wsub(r.x3, r.t0) >> 10;
             }
         }
         for (int i = 0; i < 8; i++) {
@@ -524,11 +536,11 @@ private:
             uint8_t* o = out + static_cast<size_t>(i) * static_cast<size_t>(stride);
             Idct1D r = idct1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
             const int bias = 65536 + (128 << 17);
-            r.x0 += bias; r.x1 += bias; r.x2 += bias; r.x3 += bias;
-            o[0] = clamp255((r.x0 + r.t3) >> 17); o[7] = clamp255((r.x0 - r.t3) >> 17);
-            o[1] = clamp255((r.x1 + r.t2) >> 17); o[6] = clamp255((r.x1 - r.t2) >> 17);
-            o[2] = clamp255((r.x2 + r.t1) >> 17); o[5] = clamp255((r.x2 - r.t1) >> 17);
-            o[3] = clamp255((r.x3 + r.t0) >> 17); o[4] = clamp255((r.x3 - r.t0) >> 17);
+            r.x0 = wadd(r.x0, bias); r.x1 = wadd(r.x1, bias); r.x2 = wadd(r.x2, bias); r.x3 = wadd(r.x3, bias);
+            o[0] = clamp255(wadd(r.x0, r.t3) >> 17); o[7] = clamp255(wsub(r.x0, r.t3) >> 17);
+            o[1] = clamp255(wadd(r.x1, r.t2) >> 17); o[6] = clamp255(wsub(r.x1, r.t2) >> 17);
+            o[2] = clamp255(wadd(r.x2, r.t1) >> 17); o[5] = clamp255(wsub(r.x2, r.t1) >> 17);
+            o[3] = clamp255(wadd(r.x3, r.t0) >> 17); o[4] = clamp255(wsub(r.x3, r.t0) >> 17);
         }
     }
 
@@ -630,6 +642,7 @@ private:
                                             41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
                                             15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+    const uint8_t* begin_;
     const uint8_t* p_;
     const uint8_t* end_;
     int W_ = 0, H_ = 0, hmax_ = 1, vmax_ = 1, mcuW_ = 8, mcuH_ = 8, mcusX_ = 0, mcusY_ = 0;

@@ -52,7 +52,8 @@ public:
     const Json& operator[](int i) const { return (*this)[static_cast<size_t>(i < 0 ? ~size_t(0) : static_cast<size_t>(i))]; }
     size_t size() const { return type == Array ? arr.size() : (type == Object ? obj.size() : 0); }
     double number(double dflt = 0.0) const { return type == Number ? num : dflt; }
-    int integer(int dflt = 0) const { return type == Number ? static_cast<int>(num) : dflt; }
+    int integer(int dflt = 0) const      // numbers outside int's range (or NaN) count as absent: the cast would be undefined
+    { return (type == Number && num >= -2147483648.0 && num <= 2147483647.0) ? static_cast<int>(num) : dflt; }
     const std::string& string() const { static const std::string e; return type == String ? str : e; }
 
     static Json parse(const std::string& text)

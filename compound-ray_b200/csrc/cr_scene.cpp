@@ -182,23 +182,48 @@ struct Model {
         if (t == "MAT4") return 16;
         throw std::runtime_error("gltf accessor type not supported: " + t);
     }
+    // A JSON number used as a size or offset: a non-negative integer below 2^53, or the file is rejected
+    // (casting a negative or huge double to size_t is undefined, and would wrap the range checks below).
+    static size_t sizeField(const Json& v, double dflt, const char* what)
+    {
+        const double d = v.number(dflt);
+        if (!(d >= 0.0) || d > 9007199254740992.0 || d != static_cast<double>(static_cast<uint64_t>(d)))
+            throw std::runtime_error(std::string("gltf: '") + what + "' is not a valid size");
+        return static_cast<size_t>(d);
+    }
+    const std::vector<uint8_t>& bufferOf(const Json& bv) const
+    {
+        const int b = bv["buffer"].integer(-1);
+        if (b < 0 || static_cast<size_t>(b) >= buffers.size()) throw std::runtime_error("gltf: bufferView without a valid buffer");
+        return buffers[static_cast<size_t>(b)];
+    }
     View view(int accessorIdx) const
     {
+        if (accessorIdx < 0) throw std::runtime_error("bad accessor index");
         const Json& acc = j["accessors"][static_cast<size_t>(accessorIdx)];
         if (!acc.isObject()) throw std::runtime_error("bad accessor index");
-        const Json& bv = j["bufferViews"][static_cast<size_t>(acc["bufferView"].integer(-1))];
+        const int bvIdx = acc["bufferView"].integer(-1);
+        if (bvIdx < 0) throw std::runtime_error("accessor without bufferView");
+        const Json& bv = j["bufferViews"][static_cast<size_t>(bvIdx)];
         if (!bv.isObject()) throw std::runtime_error("accessor without bufferView");
         View v;
         v.accessor = &acc;
         v.componentType = acc["componentType"].integer();
         v.ncomp = typeComponents(acc["type"].string());
-        v.count = static_cast<size_t>(acc["count"].number());
+        v.count = sizeField(acc["count"], 0, "accessor.count");
         const size_t elem = static_cast<size_t>(componentSize(v.componentType) * v.ncomp);
-        v.stride = static_cast<size_t>(bv["byteStride"].number(0));
+        v.stride = sizeField(bv["byteStride"], 0, "bufferView.byteStride");
         if (!v.stride) v.stride = elem;
-        const size_t off = static_cast<size_t>(bv["byteOffset"].number(0)) + static_cast<size_t>(acc["byteOffset"].number(0));
-        const auto& buf = buffers.at(static_cast<size_t>(bv["buffer"].integer()));
-        if (v.count && off + v.stride * (v.count - 1) + elem > buf.size()) throw std::runtime_error("accessor exceeds buffer");
+        const size_t bvOff = sizeField(bv["byteOffset"], 0, "bufferView.byteOffset");
+        const size_t accOff = sizeField(acc["byteOffset"], 0, "accessor.byteOffset");
+        const auto& buf = bufferOf(bv);
+        // off + stride*(count-1) + elem <= size, evaluated without any sum that could wrap
+        if (bvOff > buf.size() || accOff > buf.size() - bvOff) throw std::runtime_error("accessor exceeds buffer");
+        const size_t off = bvOff + accOff;
+        if (v.count) {
+            if (elem > buf.size() - off) throw std::runtime_error("accessor exceeds buffer");
+            if (v.count - 1 > (buf.size() - off - elem) / v.stride) throw std::runtime_error("accessor exceeds buffer");
+        }
         v.base = buf.data() + off;
         return v;
     }
@@ -231,10 +256,17 @@ struct LoadCtx {
     bool verbose;
     struct Material { float baseColor[4] = {1, 1, 1, 1}; int tex = -1; };
     std::vector<Material> materials;
+    size_t visits = 0;      // node visits so far: a glTF node graph is a forest, so this stays <= the node count
 };
 
-void processNode(LoadCtx& cx, const Json& node, const Mat4& parent)
+// glTF requires a strict tree; a file whose "children" form a cycle or a heavily shared DAG is rejected instead
+// of recursing without bound.
+constexpr int kMaxNodeDepth = 256;
+constexpr size_t kMaxNodeVisits = size_t(1) << 22;
+
+void processNode(LoadCtx& cx, const Json& node, const Mat4& parent, int depth = 0)
 {
+    if (depth > kMaxNodeDepth || ++cx.visits > kMaxNodeVisits) throw std::runtime_error("gltf: node hierarchy is not a tree (cycle or runaway sharing)");
     const Json& J = cx.md.j;
     const Mat4 xf = nodeTransform(parent, node);
 
@@ -426,7 +458,7 @@ void processNode(LoadCtx& cx, const Json& node, const Mat4& parent)
 
     const Json& children = node["children"];                            // MulticamScene.cpp:519-525
     for (size_t i = 0; i < children.size(); i++)
-        processNode(cx, J["nodes"][static_cast<size_t>(children[i].integer())], xf);
+        processNode(cx, J["nodes"][static_cast<size_t>(children[i].integer())], xf, depth + 1);
 }
 
 }  // namespace
@@ -497,11 +529,14 @@ HostScene loadGltfScene(const std::string& path, bool verbose)
     for (size_t i = 0; i < imgs.size(); i++) {
         std::vector<uint8_t> bytes;
         if (imgs[i].has("bufferView")) {
-            const Json& bv = J["bufferViews"][static_cast<size_t>(imgs[i]["bufferView"].integer())];
-            const auto& buf = md.buffers.at(static_cast<size_t>(bv["buffer"].integer()));
-            const size_t off = static_cast<size_t>(bv["byteOffset"].number(0));
-            const size_t len = static_cast<size_t>(bv["byteLength"].number(0));
-            if (off + len > buf.size()) throw std::runtime_error("image bufferView exceeds buffer");
+            const int bvIdx = imgs[i]["bufferView"].integer(-1);
+            if (bvIdx < 0) throw std::runtime_error("image with a bad bufferView index");
+            const Json& bv = J["bufferViews"][static_cast<size_t>(bvIdx)];
+            if (!bv.isObject()) throw std::runtime_error("image with a bad bufferView index");
+            const auto& buf = md.bufferOf(bv);
+            const size_t off = Model::sizeField(bv["byteOffset"], 0, "bufferView.byteOffset");
+            const size_t len = Model::sizeField(bv["byteLength"], 0, "bufferView.byteLength");
+            if (off > buf.size() || len > buf.size() - off) throw std::runtime_error("image bufferView exceeds buffer");
             bytes.assign(buf.begin() + static_cast<long>(off), buf.begin() + static_cast<long>(off + len));
         } else {
             bytes = loadUri(imgs[i]["uri"].string(), md.dir);
@@ -515,7 +550,7 @@ HostScene loadGltfScene(const std::string& path, bool verbose)
         sc.textures.push_back(images[static_cast<size_t>(src)]);
     }
 
-    LoadCtx cx{md, sc, verbose, {}};
+    LoadCtx cx{md, sc, verbose, {}, 0};
     const Json& mats = J["materials"];
     for (size_t i = 0; i < mats.size(); i++) {
         LoadCtx::Material m;

@@ -251,6 +251,57 @@ def test_malformed_inputs_are_reported_not_thrown(lib, tmp_path, capfd):
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/python-examples/eyeRendererHelperFunctions.py"),
                     reason="reference tree not present on this machine")
+def test_parsers_survive_fuzzed_inputs_under_sanitizers(ref_data, tmp_path):
+    """Mutated scenes and images (byte flips, numeric-token swaps, truncation, slice deletion/duplication) through
+    the glTF loader, the .eye reader and the PNG/JPEG decoders built with -fsanitize=address,undefined: every input
+    loads or is rejected with an exception; no sanitizer report.  (tools/loader_fuzz.py runs the long campaign.)"""
+    import glob
+    from tools import loader_fuzz
+    scenes = [os.path.join(ref_data, "data", "test-scene", "test-scene.gltf"), os.path.join(ref_data, "sim-environment", "env_2.gltf")]
+    images = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "png", "*.png")) + glob.glob(os.path.join(ROOT, "tests", "golden", "jpeg", "*.jpg")))
+    accepted, rejected, report = loader_fuzz.run(str(tmp_path), scenes, images, n_gltf=250, n_images=700, seed=2)
+    assert not report, report
+    assert accepted + rejected == 950 and accepted > 50 and rejected > 300, (accepted, rejected)
+
+
+def test_hostile_gltf_fields_are_rejected(lib, ref_data, tmp_path, capfd):
+    """The concrete cases the fuzzer found: sizes that wrap the accessor range check, a node that is its own child,
+    an image bufferView past the end of its buffer.  Each is an error message, not a crash, and the previously
+    loaded scene stays in place."""
+    import json
+    import shutil
+    src = os.path.join(ref_data, "data", "test-scene", "test-scene.gltf")
+    for f in ("test.eye", "test100.eye"):
+        shutil.copy(os.path.join(ref_data, "data", "test-scene", f), tmp_path / f)
+    lib.loadGlTFscene(src.encode())
+    assert lib.getCameraCount() == 6
+    base = json.load(open(src))
+
+    def attempt(mutate, what):
+        g = json.loads(json.dumps(base))
+        mutate(g)
+        p = tmp_path / "hostile.gltf"
+        p.write_text(json.dumps(g))
+        capfd.readouterr()
+        lib.loadGlTFscene(str(p).encode())
+        err = capfd.readouterr().err
+        assert "ERROR" in err and what in err, (what, err[-300:])
+        assert lib.getCameraCount() == 6, "the scene loaded before stays loaded"
+
+    attempt(lambda g: g["accessors"][0].__setitem__("count", 1e30), "not a valid size")
+    attempt(lambda g: g["accessors"][0].__setitem__("count", -1), "not a valid size")
+    attempt(lambda g: g["accessors"][0].__setitem__("byteOffset", 18446744073709551604), "not a valid size")
+    attempt(lambda g: g["bufferViews"][0].__setitem__("byteOffset", 2 ** 40), "exceeds buffer")
+    attempt(lambda g: g["accessors"][0].__setitem__("count", 10 ** 9), "exceeds buffer")
+    attempt(lambda g: g["bufferViews"][0].__setitem__("buffer", 7), "valid buffer")
+
+    def cycle(g):                                   # a root's new child that lists itself as its child
+        k = next(i for i, n in enumerate(g["nodes"]) if "children" in n)
+        g["nodes"].append({"name": "loop", "children": [len(g["nodes"])]})
+        g["nodes"][k]["children"].append(len(g["nodes"]) - 1)
+    attempt(cycle, "not a tree")
+
+
 def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
     """The reference's own ctypes helper configures and drives this library unchanged."""
     sys.path.insert(0, "/root/reference/python-examples")
