@@ -321,6 +321,7 @@ size_t Renderer::ommatidialCount()
 void Renderer::setOmmatidia(const Ommatidium* omm, size_t count)
 {
     if (!compoundActive()) return;
+    if (!omm && count) throw std::runtime_error("setOmmatidia: null table with a non-zero count");
     HostCamera& cam = camera();
     CompoundState& cs = compoundState(current_);
     if (count != cam.ommatidia.size()) cs.randomsConfigured = false;  // CompoundEye.cpp:35-48
@@ -594,7 +595,7 @@ void Renderer::saveFrame(const std::string& path)
 // ------------------------------------------------------------------------------------------
 void Renderer::copyOmmatidialData(float* outRgb)
 {
-    if (!compoundActive()) return;
+    if (!compoundActive() || !outRgb) return;
     CompoundState& cs = compoundState(current_);
     if (!cs.dSummed) return;
     std::vector<float4> tmp(static_cast<size_t>(cs.N));
@@ -612,6 +613,7 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
 {
     if (!loaded_) throw std::runtime_error("renderPoseBatch called before loadGlTFscene");
     if (!compoundActive()) throw std::runtime_error("renderPoseBatch needs an active compound eye");
+    if (!poses12 && count) throw std::runtime_error("renderPoseBatch: null pose array with a non-zero count");
     ensureDevice();
     if (!dscene_.nodes) uploadScene();
     HostCamera& cam = camera();

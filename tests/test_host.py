@@ -302,6 +302,22 @@ def test_hostile_gltf_fields_are_rejected(lib, ref_data, tmp_path, capfd):
     attempt(cycle, "not a tree")
 
 
+def test_null_arguments_are_reported(lib, ref_data, capfd):
+    """Null tables with non-zero counts are an error message (the reference would dereference them)."""
+    import ctypes as C
+    lib.loadGlTFscene(os.path.join(ref_data, "data", "test-scene", "test-scene.gltf").encode())
+    assert lib.gotoCameraByName(b"insect-cam-2")
+    n = lib.getCurrentEyeOmmatidialCount()
+    capfd.readouterr()
+    lib.setOmmatidia.argtypes = [C.c_void_p, C.c_size_t]
+    lib.setOmmatidia(None, 5)
+    assert "null table" in capfd.readouterr().err and lib.getCurrentEyeOmmatidialCount() == n
+    assert lib.crRenderPoseBatch(None, 3, None, None) == -1.0
+    assert "ERROR" in capfd.readouterr().err
+    lib.crGetOmmatidialData(None)
+    lib.getCameraPosition(None, None, None)
+
+
 def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
     """The reference's own ctypes helper configures and drives this library unchanged."""
     sys.path.insert(0, "/root/reference/python-examples")
