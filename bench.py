@@ -160,6 +160,28 @@ def traversal_counters(lib, er, S_probe=32):
             "nodes_from_root": cnt[0] / n, "tris_from_root": cnt[1] / n}
 
 
+def issue_roofline(tj, frames_per_launch, rays_per_step, rays_per_sec_per_gpu, sm_mhz, n_sms=148):
+    """Second roofline of K1, the one that binds it: warp-instruction issue slots.  The instructions one launch
+    executes were counted by ncu (profiles/k1_traffic.json, same kernel, same workload, same frames per launch);
+    achieved = that count per ray x the LIVE rays/s; peak = SMs x 4 schedulers x 1 warp instruction per clock at the
+    SM clock sampled during the timed region."""
+    try:
+        inst = float(tj["inst_executed_per_launch"])
+        if int(tj["frames_per_launch"]) != int(frames_per_launch) or not sm_mhz:
+            return None
+        per_ray = inst / (float(rays_per_step) * frames_per_launch)
+        peak = n_sms * 4 * float(sm_mhz) * 1e6
+        achieved = rays_per_sec_per_gpu * per_ray
+        return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": achieved / peak,
+                "warp_inst_per_ray": per_ray, "active_lanes_per_inst": tj.get("thread_inst_per_warp_inst"),
+                "ncu_issue_active_pct": tj.get("issue_active_pct"),
+                "note": "K1 is bound by instruction issue and load latency, not by HBM; the lanes idle inside the traversal loop "
+                        "(active_lanes_per_inst of 32) are the remaining headroom.  achieved uses the whole step's rays/s (entry "
+                        "frontier and ordered sum included), so K1 alone sits a few percent higher (ncu_issue_active_pct)"}
+    except Exception:
+        return None
+
+
 def cpu_baseline(gltf, S, target_seconds=12.0, threads=None):
     """Times the CPU oracle port (raygen + BVH traversal + shading, all host threads) on a bounded
     sample of the same workload: the first n ommatidia of the eye at S samples each."""
@@ -364,13 +386,14 @@ def main():
         peak, peak_src = measured_peak_gbs()
         achieved = (value / world) * bytes_per_ray / 1e9
         traffic = None
+        tj = {}
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
                 traffic = tj.get("dram_bytes_per_launch") if tj.get("frames_per_launch") == F else None
             except Exception:
-                traffic = None
+                traffic, tj = None, {}
         dram_gbs = (traffic / (dev_ms / K * F * 1e-3) / 1e9) if traffic else None # measured DRAM bytes (ncu) over the live launch time
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "dram_achieved_gbs": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
@@ -384,6 +407,7 @@ def main():
                             "The BVH bytes are L1/L2 hits (one viewpoint per frame): the kernel is issue/latency-bound, not HBM-bound. "
                             "dram_* = ncu-measured DRAM bytes per launch (RNG state + samples) / live launch time: the true HBM "
                             "utilisation -- see profiles/ for the ncu summaries"}
+        roofline["issue"] = issue_roofline(tj, F, rays_per_step, value / world, clocks.get("sm_mhz"))
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(gltf, S)
         out = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -40,3 +40,21 @@ def test_committed_gpu_bench_line_carries_every_contract_key():
     c = j["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "port" and c["value"] > 0
     assert "workload" in j["config"] and "l2_policy" in j["config"]
+
+
+def test_issue_roofline_from_the_committed_ncu_capture():
+    """roofline.issue: warp instructions per ray from the ncu capture x live rays/s against SMs x 4 schedulers x clock.
+    With the committed line's 20.8 Grays/s at 1965 MHz it lands a few percent under ncu's own issue-active figure
+    (the step also contains the entry-frontier and ordered-sum launches)."""
+    code = ("import sys, json; sys.argv=['bench.py']; import bench; "
+            "tj=json.load(open('profiles/k1_traffic.json')); "
+            "r=bench.issue_roofline(tj, 34, 10240000, 20.803e9, 1965.0); "
+            "bad=[bench.issue_roofline({}, 34, 10240000, 1e9, 1965.0), bench.issue_roofline(tj, 8, 10240000, 1e9, 1965.0), "
+            "bench.issue_roofline(tj, 34, 10240000, 1e9, None)]; "
+            "sys.stderr.write('RESULT ' + json.dumps([r, bad]))")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert p.returncode == 0, p.stderr[-2000:]
+    r, bad = json.loads(p.stderr.split("RESULT ", 1)[1])
+    assert bad == [None, None, None]
+    assert r["bound"] == "issue" and abs(r["peak"] - 148 * 4 * 1.965) < 1e-6 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 30 < r["warp_inst_per_ray"] < 40 and 0.5 < r["frac"] < r["ncu_issue_active_pct"] / 100
