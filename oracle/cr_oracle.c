@@ -13,7 +13,7 @@
  *   - Whole frames: pinned against six frames the reference itself rendered and its authors
  *     committed beside their scripts (python-examples/{alias-demonstration,heterogeneous-demonstration,
  *     overview-images}; tests/golden/reference_outputs.tar.gz, tests/test_reference_outputs.py): every
- *     ommatidium that sees only sky -- 1131 of them over the six frames -- is reproduced byte for byte.
+ *     ommatidium that sees only sky -- 1136 of them over the six frames -- is reproduced byte for byte.
  *     That covers .eye parsing, camera pose, RNG stream layout and draw order, the sample cone, the
  *     world transform, simple_sky, the sample average, the spherical projection, make_color and the
  *     PPM orientation.  The ground of those frames is the authors' unpublished natural environment
