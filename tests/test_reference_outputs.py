@@ -307,6 +307,63 @@ def test_product_reproduces_the_viewer_screenshot(lib, er, oracle, loader, ref_d
           f"ground {(diff[ground] == 0).mean():.4f} exact")
 
 
+# ------------------------------------------------------------------------------------------ product (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("stored", list(VARIANCE_RUNS))
+def test_product_reproduces_the_reference_variances(lib, er, oracle, loader, ref_data, ref_outputs, stored):
+    """quantified-experiment.py:76-99 through the C ABI: F consecutive renderFrame + getFramePointer calls."""
+    S, F = VARIANCE_RUNS[stored]
+    oframes, clear = oracle_vector_run(oracle, loader, ref_data, S, F)
+    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
+    assert lib.gotoCameraByName(CAMERA.encode())
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N = lib.getCurrentEyeOmmatidialCount()
+    er.setRenderSize(lib, N, 1)                                            # quantified-experiment.py:77
+    lib.setCurrentEyeSamplesPerOmmatidium(S)
+    lib.renderFrame()                                                      # "first call to ensure randoms are configured"
+    frames = np.zeros((F, N, 3), np.uint8)
+    for i in range(F):
+        lib.renderFrame()
+        frames[i] = lib.getFramePointer()[0, :, :3]
+    assert np.array_equal(frames[:, clear], oframes[:, clear]), "product and oracle agree on every frame of the sky-only ommatidia"
+    hold_to_stored_variance(script_variance(frames), clear, os.path.join(ref_outputs, stored))
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scenario", list(SCENARIOS))
+def test_product_reproduces_the_reference_frames(lib, er, oracle, loader, ref_data, ref_outputs, tmp_path, scenario):
+    """The scripts' call sequences through the C ABI; the PPM files saveFrameAs writes are held to the reference's."""
+    tables = eye_tables(er, ref_data, ref_outputs)
+    run = OracleRun(oracle, loader, ref_data, tables, scenario)            # supplies the clear-sky mask (and a cross-check)
+    (W, H), s_arg, warmup, steps = SCENARIOS[scenario]
+    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
+    er.setRenderSize(lib, W, H)
+    if scenario.startswith("viewpoint"):
+        assert lib.gotoCameraByName(CAMERA.encode())                       # viewpoint-experiment.py:40
+    else:
+        er.gotoFirstCompoundEye(lib)                                       # demonstration.py:72-83
+        assert lib.getCurrentCameraName() == CAMERA.encode()
+    lib.setCurrentEyeSamplesPerOmmatidium(s_arg)
+    assert lib.getCurrentEyeSamplesPerOmmatidium() == max(1, s_arg)
+    for _ in range(warmup):
+        lib.renderFrame()
+    checked = 0
+    for (table, stored), (oframe, pm, clear, _) in zip(steps, run.frames()):
+        if table is not None:
+            er.setOmmatidiaFromOmmatidiumList(lib, tables[table])
+        assert lib.renderFrame() > 0
+        lib.displayFrame()
+        ppm = tmp_path / (os.path.basename(stored) if stored else f"{table}.ppm")
+        lib.saveFrameAs(str(ppm).encode())
+        frame = read_ppm(str(ppm))[::-1]
+        px = clear[pm]
+        assert np.array_equal(frame[px], oframe[px]), "product and oracle agree byte for byte on sky-only ommatidia"
+        if stored:
+            checked += hold_to_stored(frame, os.path.join(ref_outputs, stored), pm, clear)
+    assert checked > 0
+
+
 # ------------------------------------------------------------------------------------------ viewer screenshot, test scene
 # docs/images/test-scene-running.png: the viewer on data/test-scene/test-scene.gltf looking through `insect-cam-1`
 # (two presses of N from camera 0; 1000 ommatidia of 2 rad acceptance, spherical_orientationwise, default_background,
@@ -378,60 +435,3 @@ def test_product_reproduces_the_test_scene_screenshot(lib, er, oracle, loader, r
     lib.renderFrame()
     assert np.array_equal(er.getFrame(lib, 400, 400)[:, :, :3], frame), "crSetFirstFrame(k) == k sequential frames"
     lib.crSetFirstFrame(0)
-
-
-# ------------------------------------------------------------------------------------------ product (GPU)
-@pytest.mark.gpu
-@pytest.mark.parametrize("stored", list(VARIANCE_RUNS))
-def test_product_reproduces_the_reference_variances(lib, er, oracle, loader, ref_data, ref_outputs, stored):
-    """quantified-experiment.py:76-99 through the C ABI: F consecutive renderFrame + getFramePointer calls."""
-    S, F = VARIANCE_RUNS[stored]
-    oframes, clear = oracle_vector_run(oracle, loader, ref_data, S, F)
-    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
-    assert lib.gotoCameraByName(CAMERA.encode())
-    lib.setCurrentEyeShaderName(b"single_dimension_fast")
-    N = lib.getCurrentEyeOmmatidialCount()
-    er.setRenderSize(lib, N, 1)                                            # quantified-experiment.py:77
-    lib.setCurrentEyeSamplesPerOmmatidium(S)
-    lib.renderFrame()                                                      # "first call to ensure randoms are configured"
-    frames = np.zeros((F, N, 3), np.uint8)
-    for i in range(F):
-        lib.renderFrame()
-        frames[i] = lib.getFramePointer()[0, :, :3]
-    assert np.array_equal(frames[:, clear], oframes[:, clear]), "product and oracle agree on every frame of the sky-only ommatidia"
-    hold_to_stored_variance(script_variance(frames), clear, os.path.join(ref_outputs, stored))
-
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("scenario", list(SCENARIOS))
-def test_product_reproduces_the_reference_frames(lib, er, oracle, loader, ref_data, ref_outputs, tmp_path, scenario):
-    """The scripts' call sequences through the C ABI; the PPM files saveFrameAs writes are held to the reference's."""
-    tables = eye_tables(er, ref_data, ref_outputs)
-    run = OracleRun(oracle, loader, ref_data, tables, scenario)            # supplies the clear-sky mask (and a cross-check)
-    (W, H), s_arg, warmup, steps = SCENARIOS[scenario]
-    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
-    er.setRenderSize(lib, W, H)
-    if scenario.startswith("viewpoint"):
-        assert lib.gotoCameraByName(CAMERA.encode())                       # viewpoint-experiment.py:40
-    else:
-        er.gotoFirstCompoundEye(lib)                                       # demonstration.py:72-83
-        assert lib.getCurrentCameraName() == CAMERA.encode()
-    lib.setCurrentEyeSamplesPerOmmatidium(s_arg)
-    assert lib.getCurrentEyeSamplesPerOmmatidium() == max(1, s_arg)
-    for _ in range(warmup):
-        lib.renderFrame()
-    checked = 0
-    for (table, stored), (oframe, pm, clear, _) in zip(steps, run.frames()):
-        if table is not None:
-            er.setOmmatidiaFromOmmatidiumList(lib, tables[table])
-        assert lib.renderFrame() > 0
-        lib.displayFrame()
-        ppm = tmp_path / (os.path.basename(stored) if stored else f"{table}.ppm")
-        lib.saveFrameAs(str(ppm).encode())
-        frame = read_ppm(str(ppm))[::-1]
-        px = clear[pm]
-        assert np.array_equal(frame[px], oframe[px]), "product and oracle agree byte for byte on sky-only ommatidia"
-        if stored:
-            checked += hold_to_stored(frame, os.path.join(ref_outputs, stored), pm, clear)
-    assert checked > 0
