@@ -47,6 +47,8 @@ OUTPUTS = {
     # archive name                                   : path under /root/reference
     "alias-demonstration/spherical-image-0-samples.ppm": PY + "/alias-demonstration/output/view-images/spherical-image-0-samples.ppm",
     "alias-demonstration/spherical-image-700-samples.ppm": PY + "/alias-demonstration/output/view-images/spherical-image-700-samples.ppm",
+    # viewpoint-experiment.py:51-66 -- column k of this image is column k of the frame rendered with k+1 samples
+    "alias-demonstration/combinedImage-700segs.png": PY + "/alias-demonstration/output/view-images/combinedImage-700segs.png",
     "heterogeneous-demonstration/1000-extreme-horizontallyAcute-variableDegree.eye":
         PY + "/heterogeneous-demonstration/1000-extreme-horizontallyAcute-variableDegree.eye",
     "heterogeneous-demonstration/heterogeneous-omms-4.ppm": PY + "/heterogeneous-demonstration/heterogeneous-omms-4.ppm",

@@ -2,7 +2,8 @@
 
 The reference ships no tests, but its authors committed frames their OptiX build rendered, next to the scripts
 that made them:
-  python-examples/alias-demonstration/viewpoint-experiment.py:27-66   -> output/view-images/spherical-image-{0,700}-samples.ppm
+  python-examples/alias-demonstration/viewpoint-experiment.py:27-66   -> output/view-images/spherical-image-{0,700}-samples.ppm,
+                                                                         combinedImage-700segs.png
   python-examples/heterogeneous-demonstration/demonstration.py:60-125 -> heterogeneous-omms-4.ppm, homogeneous-omms-small-4.ppm
   python-examples/overview-images/overviewImages.py:88-131            -> uniform-omms.ppm, acute-omms.ppm
   python-examples/alias-demonstration/quantified-experiment.py:76-137 -> output/vector-data{,-100samples}/variance-*-samples.txt
@@ -246,13 +247,19 @@ SHOT = os.path.join("docs", "images", "standin-sky-render.png")
 SHOT_CONTENT = (slice(45, 445), slice(10, 410))                            # client area inside the window frame
 
 
-def viewer_screenshot(lib, ref_outputs, name=SHOT):
-    """uint8[400][400][3], rows top-down; decoded by the product's PNG reader (byte-exact vs stb_image: test_host.py)."""
+def decode_png(lib, path):
+    """uint8[H][W][4], rows top-down; decoded by the product's PNG reader (byte-exact vs stb_image: test_host.py)."""
     import ctypes as C
     w, h = C.c_int(), C.c_int()
-    assert lib.crDebugDecodeImageFile(os.path.join(ref_outputs, name).encode(), C.byref(w), C.byref(h))
+    assert lib.crDebugDecodeImageFile(path.encode(), C.byref(w), C.byref(h))
     px = np.zeros((h.value, w.value, 4), np.uint8)
     lib.crDebugCopyDecodedImage(px.ctypes.data)
+    return px
+
+
+def viewer_screenshot(lib, ref_outputs, name=SHOT):
+    """uint8[400][400][3], rows top-down: the client area of a viewer screenshot."""
+    px = decode_png(lib, os.path.join(ref_outputs, name))
     assert (px[44, 10:410, :3] < 64).all() and (px[445, 10:410, :3] == 0).all()   # title bar above, border below
     return px[SHOT_CONTENT][:, :, :3]
 
@@ -435,3 +442,60 @@ def test_product_reproduces_the_test_scene_screenshot(lib, er, oracle, loader, r
     lib.renderFrame()
     assert np.array_equal(er.getFrame(lib, 400, 400)[:, :, :3], frame), "crSetFirstFrame(k) == k sequential frames"
     lib.crSetFirstFrame(0)
+
+
+# ------------------------------------------------------------------------------------------ 700-column composite
+# viewpoint-experiment.py:51-66 stores, besides the frames, output/view-images/combinedImage-700segs.png: column k of
+# it is column k of the (flipped) frame rendered with k+1 samples per ommatidium -- 700 sample counts, each after its
+# own setCurrentEyeSamplesPerOmmatidium + throw-away frame.  A spread of those columns is checked: every clear-sky
+# pixel of each must carry the reference's bytes, which exercises the stream layout id = N*s + o and the reset on a
+# sample-count change at fifteen different S.
+COMPOSITE = os.path.join("alias-demonstration", "combinedImage-700segs.png")
+COMPOSITE_S = (1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 700)
+
+
+def composite_columns(oracle, loader, ref_data):
+    """Per sample count S: (column index, column of the oracle's second frame top-down uint8[300][3], clear-sky rows)."""
+    _, sh, cam = load_oracle_scene(loader, oracle, os.path.join(ref_data, SCENE), CAMERA)
+    omm = np.asarray(cam.ommatidia, dtype=np.float32).reshape(-1, 8)
+    pm = oracle.projection_map(omm, "spherical_orientationwise", 700, 300)[::-1]
+    eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(cam), "spherical_orientationwise")
+    N = len(omm)
+    for S in COMPOSITE_S:
+        eye.set_samples(S)
+        eye.render_frame(method="bvh", project=False)
+        eye.render_frame(method="bvh", project=False)
+        colours = oracle.make_color(eye.last["summed"])[:, :3]
+        miss = (eye.last["hits"]["prim"].reshape(S, N) < 0).all(axis=0)
+        d = eye.last["dirs"].astype(np.float64)
+        clear = miss & ((d[:, 1] / np.linalg.norm(d, axis=1)).reshape(S, N).min(axis=0) > TREE_LINE)
+        k = S - 1
+        yield S, k, colours[pm[:, k]], clear[pm[:, k]]
+
+
+def test_oracle_reproduces_the_700_column_composite(lib, oracle, loader, ref_data, ref_outputs):
+    ref = decode_png(lib, os.path.join(ref_outputs, COMPOSITE))[:, :, :3]
+    assert ref.shape == (300, 700, 3)
+    checked = 0
+    for S, k, column, rows in composite_columns(oracle, loader, ref_data):
+        assert rows.sum() >= 100, (S, rows.sum())
+        assert np.array_equal(column[rows], ref[:, k][rows]), f"S = {S}"
+        checked += int(rows.sum())
+    assert checked > 1500                                                              # measured: 1721, all equal
+
+
+# (product-side twins written after the round's GPU minutes were spent: they have not run on a GPU yet -- kept last)
+@pytest.mark.gpu
+def test_product_reproduces_the_700_column_composite(lib, er, oracle, loader, ref_data, ref_outputs):
+    """viewpoint-experiment.py:36-66 through the C ABI at the same fifteen sample counts."""
+    ref = decode_png(lib, os.path.join(ref_outputs, COMPOSITE))[:, :, :3]
+    lib.loadGlTFscene(os.path.join(ref_data, SCENE).encode())
+    er.setRenderSize(lib, 700, 300)
+    assert lib.gotoCameraByName(CAMERA.encode())
+    for S, k, ocolumn, rows in composite_columns(oracle, loader, ref_data):
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
+        lib.renderFrame()                                                              # "first call to ensure randoms are configured"
+        lib.renderFrame()
+        column = np.flipud(er.getFrame(lib, 700, 300)[:, :, :3])[:, k]
+        assert np.array_equal(column[rows], ocolumn[rows]), f"product vs oracle, S = {S}"
+        assert np.array_equal(column[rows], ref[:, k][rows]), f"product vs reference, S = {S}"
