@@ -6,6 +6,7 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
                          a box without /root/reference.  No reference source code is included.
   xorwow_kat.json        cuRAND's own host XORWOW implementation (oracle/_ref/curand_kat)
   sutil_kat.json         the reference's sutil math headers evaluated on fixed inputs (oracle/_ref/sutil_kat)
+  hitscan_kat.json       the reference's sutil/hitscanprocessing.cpp (point-in-hitbox, bounds) on three meshes x 400 points
   jpeg/*.jpg             small JPEG test streams written with PIL (4:4:4 / 4:2:2 / 4:2:0 / grey / progressive)
   stb_jpeg_kat.{json,npz} those streams decoded by the reference's vendored stb_image.h (oracle/_ref/stb_kat)
   png/*.png              small PNG streams of every colour type / bit depth / tRNS form, plain and Adam7 (own writer)
@@ -255,6 +256,8 @@ def main():
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "curand_kat")], stdout=f)
     with open(os.path.join(HERE, "sutil_kat.json"), "w") as f:
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sutil_kat")], stdout=f)
+    with open(os.path.join(HERE, "hitscan_kat.json"), "w") as f:
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "hitscan_kat")], stdout=f)
     make_jpeg_kat()
     make_png_kat()
     pack(os.path.join(HERE, "reference_data.tar.gz"), FILES)

@@ -223,6 +223,36 @@ def test_hit_geometry_queries(lib, tmp_path):
     assert not lib.isInsideHitGeometry(0, 0, 0, b"missing")
 
 
+def test_hit_geometry_queries_match_the_reference_hitscan(lib, tmp_path):
+    """isInsideHitGeometry / getGeometry{Min,Max}Bounds against the reference's own sutil/hitscanprocessing.cpp
+    (compiled where it lies by oracle/kat/hitscan_kat.cpp -> tests/golden/hitscan_kat.json): a cube, a rotated and
+    non-uniformly scaled tetrahedron and a non-convex L-shaped prism, 400 query points each; bounds bit-exact."""
+    import base64
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hitscan_kat.json")))
+    assert set(gold) == {"cube", "tetra", "ell"}
+    for name, case in gold.items():
+        v = np.array(case["verts"], np.float32)
+        idx = np.array(case["idx"], np.uint16)
+        blob = v.tobytes() + idx.tobytes()
+        gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}],
+                "nodes": [{"mesh": 0, "name": "n", "translation": case["t"], "rotation": case["r"], "scale": case["s"]}],
+                "meshes": [{"name": name, "extras": {"hitbox": True}, "primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+                "accessors": [{"bufferView": 0, "componentType": 5126, "count": len(v), "type": "VEC3"},
+                              {"bufferView": 1, "componentType": 5123, "count": len(idx), "type": "SCALAR"}],
+                "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": v.nbytes}, {"buffer": 0, "byteOffset": v.nbytes, "byteLength": idx.nbytes}],
+                "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+        p = tmp_path / f"{name}.gltf"
+        p.write_text(json.dumps(gltf))
+        lib.loadGlTFscene(str(p).encode())
+        lo, hi = lib.getGeometryMinBounds(name.encode()), lib.getGeometryMaxBounds(name.encode())
+        got = np.array([lo.x, lo.y, lo.z, hi.x, hi.y, hi.z], np.float32).view(np.uint32)
+        assert got.tolist() == case["world_min"] + case["world_max"], name
+        pts = np.array(case["points"], np.uint32).view(np.float32)
+        inside = [int(lib.isInsideHitGeometry(float(x), float(y), float(z), name.encode())) for x, y, z in pts]
+        assert inside == case["inside"], (name, int(np.sum(np.array(inside) != np.array(case["inside"]))))
+        assert 20 < sum(inside) < 200
+
+
 def test_no_cpu_fallback_render_fails_loudly(ref_data):
     """Without a CUDA device renderFrame reports an error and returns 0 -- it never renders on the CPU."""
     code = f"""
