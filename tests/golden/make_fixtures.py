@@ -7,6 +7,8 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
   xorwow_kat.json        cuRAND's own host XORWOW implementation (oracle/_ref/curand_kat)
   sutil_kat.json         the reference's sutil math headers evaluated on fixed inputs (oracle/_ref/sutil_kat)
   hitscan_kat.json       the reference's sutil/hitscanprocessing.cpp (point-in-hitbox, bounds) on three meshes x 400 points
+  tinygltf_kat.json      the reference's vendored tinygltf + stb_image + sutil on its own scenes: cameras in insertion order
+                         with pose bits, per-primitive facts and digests of world-space triangles / UVs / colours, texture digests
   jpeg/*.jpg             small JPEG test streams written with PIL (4:4:4 / 4:2:2 / 4:2:0 / grey / progressive)
   stb_jpeg_kat.{json,npz} those streams decoded by the reference's vendored stb_image.h (oracle/_ref/stb_kat)
   png/*.png              small PNG streams of every colour type / bit depth / tRNS form, plain and Adam7 (own writer)
@@ -258,6 +260,12 @@ def main():
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sutil_kat")], stdout=f)
     with open(os.path.join(HERE, "hitscan_kat.json"), "w") as f:
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "hitscan_kat")], stdout=f)
+    with open(os.path.join(HERE, "tinygltf_kat.json"), "w") as f:      # keys = archive names of reference_data.tar.gz
+        args = []
+        for arc, src in sorted(FILES.items()):
+            if arc.endswith(".gltf"):
+                args += [arc, os.path.join(REF, src)]
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "tinygltf_kat")] + args, stdout=f, cwd="/")
     make_jpeg_kat()
     make_png_kat()
     pack(os.path.join(HERE, "reference_data.tar.gz"), FILES)

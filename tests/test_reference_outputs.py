@@ -374,13 +374,13 @@ def test_product_reproduces_the_reference_frames(lib, er, oracle, loader, ref_da
 # ------------------------------------------------------------------------------------------ viewer screenshot, test scene
 # docs/images/test-scene-running.png: the viewer on data/test-scene/test-scene.gltf looking through `insect-cam-1`
 # (two presses of N from camera 0; 1000 ommatidia of 2 rad acceptance, spherical_orientationwise, default_background,
-# vertex-coloured meshes) at 400x400.  Neither the sample count nor the frame number is recorded with the figure.
+# base-colour meshes) at 400x400.  Neither the sample count nor the frame number is recorded with the figure.
 # PAGE_UP adds 10 samples (newGuiEyeRenderer/gui.cpp:35-36) and every change restarts the streams, so the candidates
 # are S = 1, 11, 21, ... and a frame count since the last change.  A search (60 ommatidia, S in 1..41, 30 000 frames
 # each; best near-miss 18 % of the cells) found exactly one pair at which EVERY cell matches: S = 41, frame 8248.
 # There all 1000 ommatidia have the screenshot's colour byte for byte and 6 of 160 000 pixels differ (cell borders):
 # a known answer for the stream positions after 8 248 frames (3+1 draws per frame pair), wide-cone sample directions,
-# __miss__default_background (atan2/asin), closest hits on the vertex-coloured meshes (159 ommatidia see geometry),
+# __miss__default_background (atan2/asin), closest hits on the scene's meshes (159 ommatidia see geometry),
 # the 41-sample average, the projection and make_color.
 SHOT_TEST_SCENE = os.path.join("docs", "images", "test-scene-running.png")
 SHOT_S, SHOT_FRAME = 41, 8248
