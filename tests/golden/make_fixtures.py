@@ -265,6 +265,10 @@ def main():
         for arc, src in sorted(FILES.items()):
             if arc.endswith(".gltf"):
                 args += [arc, os.path.join(REF, src)]
+        # + a hand-made scene covering what the reference's scenes do not: a matrix node above TRS nodes, interleaved
+        # attributes (byteStride), u32 indices, accessor byteOffset, u16 and float COLOR_0, a non-indexed primitive,
+        # baseColorFactor, an external-file and a data-URI image, an orthographic camera under a rotated parent
+        args += ["synthetic/features.gltf", os.path.join(HERE, "synthetic", "features.gltf")]
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "tinygltf_kat")] + args, stdout=f, cwd="/")
     make_jpeg_kat()
     make_png_kat()

@@ -128,14 +128,19 @@ def _fnv(data: bytes) -> str:
 
 
 @pytest.mark.parametrize("rel", ["data/test-scene/test-scene.gltf", "data/test-scene/test-scene-sky.gltf",
-                                 "data/natural-standin-sky.gltf", "sim-environment/env_2.gltf"])
+                                 "data/natural-standin-sky.gltf", "sim-environment/env_2.gltf", "synthetic/features.gltf"])
 def test_loader_matches_the_reference_tinygltf_and_sutil(lib, ref_data, rel):
     """The product's loader against the reference's OWN parser stack -- vendored tinygltf (JSON, base64, accessors,
     materials), stb_image (textures) and sutil (node transforms) compiled where they lie by oracle/kat/tinygltf_kat.cpp:
     cameras in insertion order with pose bits, per-primitive counts and material facts, and digests of the world-space
-    triangles (v0, e1, e2), corner UVs and textures.  (tests/golden/tinygltf_kat.json)"""
+    triangles (v0, e1, e2), corner UVs, corner colours and textures (tests/golden/tinygltf_kat.json).  Besides the
+    reference's four scenes, tests/golden/synthetic/features.gltf covers what they do not exercise: a matrix node above
+    TRS nodes, interleaved attributes (byteStride), u32 indices, accessor byteOffset, u16 and float COLOR_0 (with the
+    reference shader's `/= 65535` evaluated by sutil), a non-indexed primitive, baseColorFactor, an external-file and a
+    data-URI image, an orthographic camera under a rotated parent."""
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "tinygltf_kat.json")))[rel]
-    lib.loadGlTFscene(os.path.join(ref_data, rel).encode())
+    base_dir = os.path.join(ROOT, "tests", "golden") if rel.startswith("synthetic/") else ref_data
+    lib.loadGlTFscene(os.path.join(base_dir, rel).encode())
     kinds = {0: "perspective", 1: "panoramic", 2: "orthographic", 3: "compound"}
     assert lib.getCameraCount() == len(gold["cameras"])
     for i, cam in enumerate(gold["cameras"]):
