@@ -7,6 +7,7 @@ where /root/reference and the CUDA toolkit exist; the GPU box has neither the re
   xorwow_kat.json        cuRAND's own host XORWOW implementation (oracle/_ref/curand_kat)
   sutil_kat.json         the reference's sutil math headers evaluated on fixed inputs (oracle/_ref/sutil_kat)
   hitscan_kat.json       the reference's sutil/hitscanprocessing.cpp (point-in-hitbox, bounds) on three meshes x 400 points
+  helper_kat.json        the reference's eyeRendererHelperFunctions.py (pure-Python parts) evaluated on fixed inputs
   tinygltf_kat.json      the reference's vendored tinygltf + stb_image + sutil on its own scenes: cameras in insertion order
                          with pose bits, per-primitive facts and digests of world-space triangles / UVs / colours, texture digests
   jpeg/*.jpg             small JPEG test streams written with PIL (4:4:4 / 4:2:2 / 4:2:0 / grey / progressive)
@@ -81,6 +82,29 @@ def pack(out, files):
             with open(os.path.join(REF, src), "rb") as fh:
                 tar.addfile(info, fh)
     print(out, os.path.getsize(out), "bytes")
+
+
+def make_helper_kat():
+    """helper_kat.json: the reference's own python-examples/eyeRendererHelperFunctions.py evaluated here (pure Python,
+    no renderer needed): getIcoOmmatidia, getSolidAngle, saveEyeFile's text, readEyeFile, decodeProjectionMapID."""
+    import json
+    import sys
+    import tempfile
+    sys.path.insert(0, os.path.join(REF, "python-examples"))
+    import eyeRendererHelperFunctions as R
+    ico = R.getIcoOmmatidia()
+    with tempfile.TemporaryDirectory() as tmp:
+        R.saveEyeFile(os.path.join(tmp, "ico.eye"), ico)
+        text = open(os.path.join(tmp, "ico.eye")).read()
+    eye = R.readEyeFile(os.path.join(REF, "data", "test-scene", "test100.eye"))
+    out = {"ico": [[float(v).hex() for v in (*o.position, *o.direction, o.acceptanceAngle, o.focalpointOffset)] for o in ico],
+           "ico_solid_angles": [o.getSolidAngle().hex() for o in ico],
+           "ico_eye_file": text,
+           "test100_rows": [[float(v).hex() for v in (*o.position, *o.direction, o.acceptanceAngle, o.focalpointOffset)] for o in eye[:5] + eye[-2:]],
+           "test100_solid_angles": [o.getSolidAngle().hex() for o in eye[:5]],
+           "decode_ids": [[q, R.decodeProjectionMapID(q)] for q in ([0, 0, 0, 0], [1, 2, 3, 4], [0, 0, 3, 231], [255, 255, 255, 255])]}
+    with open(os.path.join(HERE, "helper_kat.json"), "w") as f:
+        json.dump(out, f, indent=1)
 
 
 def make_jpeg_kat():
@@ -270,6 +294,7 @@ def main():
         # baseColorFactor, an external-file and a data-URI image, an orthographic camera under a rotated parent
         args += ["synthetic/features.gltf", os.path.join(HERE, "synthetic", "features.gltf")]
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "tinygltf_kat")] + args, stdout=f, cwd="/")
+    make_helper_kat()
     make_jpeg_kat()
     make_png_kat()
     pack(os.path.join(HERE, "reference_data.tar.gz"), FILES)

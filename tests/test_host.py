@@ -408,6 +408,22 @@ def test_null_arguments_are_reported(lib, ref_data, capfd):
     lib.getCameraPosition(None, None, None)
 
 
+def test_python_helper_mirror_equals_the_reference_helper(er, ref_data, tmp_path):
+    """compound-ray_b200/eye_renderer.py against values produced by the reference's own helper module
+    (tests/golden/helper_kat.json): icosahedral eye, solid angles, the .eye text writer and reader, id decoding -- exact."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "helper_kat.json")))
+    row = lambda o: [float(v).hex() for v in (*o.position, *o.direction, o.acceptanceAngle, o.focalpointOffset)]
+    ico = er.getIcoOmmatidia()
+    assert [row(o) for o in ico] == gold["ico"]
+    assert [o.getSolidAngle().hex() for o in ico] == gold["ico_solid_angles"]
+    er.saveEyeFile(str(tmp_path / "ico.eye"), ico)
+    assert (tmp_path / "ico.eye").read_text() == gold["ico_eye_file"]
+    eye = er.readEyeFile(os.path.join(ref_data, "data", "test-scene", "test100.eye"))
+    assert [row(o) for o in eye[:5] + eye[-2:]] == gold["test100_rows"]
+    assert [o.getSolidAngle().hex() for o in eye[:5]] == gold["test100_solid_angles"]
+    assert [[q, er.decodeProjectionMapID(q)] for q, _ in gold["decode_ids"]] == gold["decode_ids"]
+
+
 def test_unmodified_reference_helper_binds_to_the_library(lib, ref_data):
     """The reference's own ctypes helper configures and drives this library unchanged."""
     sys.path.insert(0, "/root/reference/python-examples")
