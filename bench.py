@@ -6,9 +6,15 @@ Workload (config.workload): BASELINE.json configs[3] headline -- synthetic speed
 ~1M triangles (per-vertex u16 colours, simple_sky) seen by a 10 000-ommatidia Fibonacci eye,
 S samples per ommatidium, projection single_dimension_fast.  A "step" is one frame = N*S rays.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--triangles T] [--ommatidia N]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--repeats R] [--mode fused|ordered|fused_fast|ordered_fast]
+                  [--samples S] [--triangles T] [--ommatidia N]
   python bench.py --impl reference ...     CPU oracle port on the host cores (the reference has no
                                            CPU renderer and its OptiX build cannot be built here)
+
+Timing: W untimed warm-up frames, then R batches of EXACTLY K frames; every batch is bracketed by a barrier and a
+device synchronisation and timed with CUDA events on the library's stream (plus torch events around the NCCL
+all-gather for N > 1), maximum over ranks per batch; `value` and `ms_per_step` come from the MEDIAN batch, all R
+batch times are listed in `batch_ms`.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -22,6 +28,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -38,14 +45,26 @@ BENCH_DIR = os.environ.get("CR_BENCH_DIR", "/tmp/crb200_bench")
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
+# crSetRenderMode(fused, fast) per named mode.  "ordered" = the reference's sequential sum and cr_math: every bit equal
+# to the checker.  "fused" (headline) = same rays/hits/colours, in-kernel reduction in a fixed order the checker restates.
+MODES = {"ordered": (0, 0), "fused": (1, 0), "fused_fast": (1, 1), "ordered_fast": (0, 1)}
+KERNEL_OF_MODE = {"ordered": "k_traceCompound<false,true,false,false>", "fused": "k_traceCompound<false,true,true,false>",
+                  "fused_fast": "k_traceCompound<false,true,true,true>", "ordered_fast": "k_traceCompound<false,true,false,true>"}
+
 
 def emit(obj):
     os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
-L2_BYTES = 126e6
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def measured_peak_gbs():
@@ -132,9 +151,10 @@ def poses_for(cam_pos, axes, count, first_index):
 
 def traversal_counters(lib, er, S_probe=32):
     """Per-ray BVH nodes fetched / triangles tested, counted ON THE DEVICE by the dump variant of the trace
-    kernel (same code path, entry frontier included) on a probe frame of S_probe samples, plus the same
-    figures for a plain root-to-leaf traversal counted by the CPU oracle's instrumented walk of the IDENTICAL
-    device BVH on the product's own rays (which also re-checks the hit ids)."""
+    kernel (same code path: entry frontier and warp packets included; a lane counts a node only when its own ray
+    reached it) on a probe frame of S_probe samples, plus the same figures for a plain root-to-leaf walk counted by
+    the CPU oracle's instrumented traversal of the IDENTICAL device BVH on the product's own rays (which also
+    re-checks the hit ids)."""
     from oracle import oracle as O
     N = lib.getCurrentEyeOmmatidialCount()
     S_keep = lib.getCurrentEyeSamplesPerOmmatidium()
@@ -154,99 +174,137 @@ def traversal_counters(lib, er, S_probe=32):
     lib.crDebugCopyBvh(nodes.ctypes.data, tris.ctypes.data)
     tm = np.zeros(n, np.float32)
     hits, cnt = O.trace_device_bvh(nodes, tris, o, d, tm)
-    assert np.array_equal(hits["prim"], h[:, 0]), "oracle traversal of the device BVH disagrees with the kernel"
+    hit_ids_equal = bool(np.array_equal(hits["prim"], h[:, 0]))
     lib.setCurrentEyeSamplesPerOmmatidium(S_keep)
-    return {"nodes": float(cnt_dev[:, 0].mean()), "tris": float(cnt_dev[:, 1].mean()), "hit_fraction": float((h[:, 0] >= 0).mean()),
-            "nodes_from_root": cnt[0] / n, "tris_from_root": cnt[1] / n}
+    hit = h[:, 0] >= 0
+    trav = cnt_dev[:, 0] > 0
+    return {"nodes": float(cnt_dev[:, 0].mean()), "tris": float(cnt_dev[:, 1].mean()), "hit_fraction": float(hit.mean()),
+            "traversing_fraction": float(trav.mean()),
+            "nodes_per_traversing_ray": float(cnt_dev[trav, 0].mean()) if trav.any() else 0.0,
+            "tris_per_traversing_ray": float(cnt_dev[trav, 1].mean()) if trav.any() else 0.0,
+            "nodes_from_root": cnt[0] / n, "tris_from_root": cnt[1] / n, "hit_ids_equal_oracle_walk": hit_ids_equal}
 
 
-def issue_roofline(tj, frames_per_launch, rays_per_step, rays_per_sec_per_gpu, sm_mhz, n_sms=148):
-    """Second roofline of K1, the one that binds it: warp-instruction issue slots.  The instructions one launch
-    executes were counted by ncu (profiles/k1_traffic.json, same kernel, same workload, same frames per launch);
-    achieved = that count per ray x the LIVE rays/s; peak = SMs x 4 schedulers x 1 warp instruction per clock at the
-    SM clock sampled during the timed region."""
+def ncu_model(mode, F):
+    """Per-launch DRAM bytes and warp instructions of the trace kernel at F frames per launch, from the committed ncu
+    captures (profiles/k1_traffic.json: `--set full --clock-control none` launches of this kernel on this workload at
+    two or more F).  Both quantities are affine in F (a per-launch term -- the RNG state read and written once -- plus
+    a per-frame term), so a line through the captures reconstructs any F the driver picks."""
     try:
-        inst = float(tj["inst_executed_per_launch"])
-        if int(tj["frames_per_launch"]) != int(frames_per_launch) or not sm_mhz:
-            return None
-        per_ray = inst / (float(rays_per_step) * frames_per_launch)
-        peak = n_sms * 4 * float(sm_mhz) * 1e6
-        achieved = rays_per_sec_per_gpu * per_ray
-        return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": achieved / peak,
-                "warp_inst_per_ray": per_ray, "active_lanes_per_inst": tj.get("thread_inst_per_warp_inst"),
-                "ncu_issue_active_pct": tj.get("issue_active_pct"),
-                "note": "K1 is bound by instruction issue and load latency, not by HBM; the lanes idle inside the traversal loop "
-                        "(active_lanes_per_inst of 32) are the remaining headroom.  achieved uses the whole step's rays/s (entry "
-                        "frontier and ordered sum included), so K1 alone sits a few percent higher (ncu_issue_active_pct)"}
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        caps = sorted(tj["modes"][mode]["captures"], key=lambda c: c["frames_per_launch"])
     except Exception:
         return None
+    if not caps:
+        return None
+
+    def at(key):
+        xs = np.array([c["frames_per_launch"] for c in caps], float)
+        ys = np.array([c[key] for c in caps], float)
+        if len(caps) == 1 or np.ptp(xs) == 0:
+            return float(ys[0] * F / xs[0])
+        b, a = np.polyfit(xs, ys, 1)
+        return float(a + b * F)
+
+    near = min(caps, key=lambda c: abs(c["frames_per_launch"] - F))
+    return {"dram_bytes": at("dram_bytes"), "inst_executed": at("inst_executed"),
+            "issue_active_pct": near.get("issue_active_pct"), "thread_inst_per_warp_inst": near.get("thread_inst_per_warp_inst"),
+            "captures_at_frames_per_launch": [c["frames_per_launch"] for c in caps], "source": tj["modes"][mode].get("source"),
+            "model": "exact capture" if any(c["frames_per_launch"] == F for c in caps) else
+                     ("line through the captures" if len(caps) > 1 else "proportional to the single capture")}
 
 
-def cpu_baseline(gltf, S, target_seconds=12.0, threads=None):
-    """Times the CPU oracle port (raygen + BVH traversal + shading, all host threads) on a bounded
-    sample of the same workload: the first n ommatidia of the eye at S samples each."""
-    from oracle import gltf_loader, oracle as O
-    sc = gltf_loader.load_scene(gltf)
-    sh = O.SceneHandle(sc)
-    cam = [c for c in sc.cameras if c.kind == "compound"][0]
-    if threads:
-        O.lib().cro_set_num_threads(int(threads))
-    cores = O.lib().cro_num_threads()
-    t0 = time.perf_counter(); sh.bvh(); build_s = time.perf_counter() - t0
-    pose = O.pose_from_camera(cam)
-
-    def run(n_omm):
-        sub = cam.ommatidia[::max(1, len(cam.ommatidia) // n_omm)][:n_omm]     # evenly strided: unbiased in direction
-        eye = O.CompoundEyeOracle(sh, sub, pose, "single_dimension_fast", samples=S)
-        eye.set_render_size(n_omm, 1)
-        eye.render_frame(method="bvh", project=False)        # frame 0 pays the stream initialisation
-        t = time.perf_counter()
-        eye.render_frame(method="bvh", project=False)
-        return n_omm * S / (time.perf_counter() - t)
-
-    n0 = max(1, min(len(cam.ommatidia), 65536 // S or 1))
-    rate = run(n0)
-    n1 = int(max(n0, min(len(cam.ommatidia), rate * target_seconds / S)))
-    rate = run(n1)
-    return {"value": rate, "unit": "rays/s", "cores": int(cores), "kind": "port",
-            "sample": f"{n1} evenly strided of {len(cam.ommatidia)} ommatidia x {S} samples = {n1 * S} rays, 1 frame after RNG init "
-                      f"(oracle BVH build {build_s:.2f} s excluded)"}
+def sample_checksum(O, sh, cam, S):
+    """CRC of the float RGB of a fixed small frame (64 strided ommatidia, frame 0): equal for every build / thread count."""
+    sub = cam.ommatidia[::max(1, len(cam.ommatidia) // 64)][:64]
+    eye = O.CompoundEyeOracle(sh, sub, O.pose_from_camera(cam), "single_dimension_fast", samples=S)
+    eye.set_render_size(len(sub), 1)
+    eye.render_frame(method="bvh", project=False)
+    return zlib.crc32(eye.last["summed"].tobytes())
 
 
 def run_reference(args):
-    """--impl reference: the reference has no CPU implementation of this path and its OptiX build
-    cannot be compiled here (no OptiX SDK), so this arm times the CPU oracle port."""
+    """--impl reference: the reference has no CPU implementation of this path and its OptiX build cannot be compiled
+    here (no OptiX SDK), so this arm times the CPU oracle port: the SAME source as the checker, compiled on
+    the machine it is timed on with `gcc -O3 -march=native` (no contraction, no fast-math: same bits), on all host
+    threads (OMP_NUM_THREADS is overridden: torchrun sets it to 1).  A step = one frame of a bounded sample of the
+    workload; the value is the median step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     gltf, _ = make_workload(args.triangles, args.ommatidia)
+    build = "portable build (gcc -O2 -march=x86-64-v3)"
+    if not args.ref_portable:
+        from oracle import oracle as O0
+        native = O0.build_native(BENCH_DIR)
+        if native:
+            os.environ["CR_ORACLE_SO"] = native
+            build = "gcc -O3 -march=native -ffp-contract=off, compiled on this host"
     from oracle import gltf_loader, oracle as O
+    threads = int(args.ref_threads) if args.ref_threads else host_threads()
+    O.lib().cro_set_num_threads(threads)
+    cores = O.lib().cro_num_threads()
     sc = gltf_loader.load_scene(gltf)
     sh = O.SceneHandle(sc)
     cam = [c for c in sc.cameras if c.kind == "compound"][0]
     sh.bvh()
-    cores = O.lib().cro_num_threads()
+    crc = sample_checksum(O, sh, cam, min(args.samples, 64))
     n_omm = max(1, min(len(cam.ommatidia), int(args.ref_rays_per_step // args.samples) or 1))
     sub = cam.ommatidia[::max(1, len(cam.ommatidia) // n_omm)][:n_omm]         # evenly strided: unbiased in direction
     eye = O.CompoundEyeOracle(sh, sub, O.pose_from_camera(cam), "single_dimension_fast", samples=args.samples)
     eye.set_render_size(n_omm, 1)
     for _ in range(max(args.warmup, 1)):
         eye.render_frame(method="bvh")
-    t0 = time.perf_counter()
+    step_s = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         eye.render_frame(method="bvh")
-    dt = time.perf_counter() - t0
-    rays = n_omm * args.samples * args.steps
-    val = rays / dt
-    sample = f"{n_omm} evenly strided of {len(cam.ommatidia)} ommatidia x {args.samples} samples per step"
+        step_s.append(time.perf_counter() - t0)
+    med = float(np.median(step_s))
+    rays = n_omm * args.samples
+    val = rays / med
+    sample = (f"{n_omm} evenly strided of {len(cam.ommatidia)} ommatidia x {args.samples} samples = {rays} rays per step; "
+              f"median of {args.steps} steps after {max(args.warmup, 1)} warm-up; {build}")
     out = {"impl": "reference", "metric": "rays_per_sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config(args),
            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": int(cores), "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0, "ommatidia_frames_per_sec": val / args.samples}
+           "gpu_launches": 0, "ommatidia_frames_per_sec": val / args.samples, "step_ms": [1e3 * s for s in step_s],
+           "sample_rgb_crc32": crc, "host_threads_available": host_threads()}
     emit(out)
+
+
+def cpu_baseline(args):
+    """The reference arm above, run twice as a subprocess (so the timing build and thread count cannot leak into this
+    process): single-threaded and on all host threads, median of 3 steps each."""
+    def run(threads, rays):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+               "--triangles", str(args.triangles), "--ommatidia", str(args.ommatidia), "--samples", str(args.samples),
+               "--ref-threads", str(threads), "--ref-rays-per-step", str(rays)]
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    try:
+        one = run(1, 1.0e6)
+        n = host_threads()
+        allc = run(n, min(float(args.ommatidia * args.samples), max(2.0e6, one["value"] * n * 2.0)))
+        from oracle import gltf_loader, oracle as O          # the portable checker build, in THIS process: same bits?
+        gltf, _ = make_workload(args.triangles, args.ommatidia)
+        sc = gltf_loader.load_scene(gltf)
+        crc = sample_checksum(O, O.SceneHandle(sc), [c for c in sc.cameras if c.kind == "compound"][0], min(args.samples, 64))
+        cb = dict(allc["cpu_baseline"])
+        cb["single_thread"] = {"value": one["value"], "cores": one["cpu_baseline"]["cores"], "sample": one["cpu_baseline"]["sample"],
+                               "step_ms": one["step_ms"]}
+        cb["step_ms"] = allc["step_ms"]
+        cb["repetitions"] = 3
+        cb["same_bits_as_checker_build"] = bool(crc == allc["sample_rgb_crc32"] == one["sample_rgb_crc32"])
+        return cb
+    except Exception as e:          # the baseline is a reported figure; it must not take the GPU numbers down with it
+        return {"value": None, "unit": "rays/s", "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
 
 def workload_config(args):
@@ -254,22 +312,27 @@ def workload_config(args):
                         f"{args.ommatidia}-ommatidia Fibonacci eye, S={args.samples}, single_dimension_fast",
             "triangles": args.triangles, "ommatidia": args.ommatidia, "samples_per_ommatidium": args.samples,
             "rays_per_step": args.ommatidia * args.samples,
-            "l2_policy": "inputs larger than L2: RNG state %.0f MB + samples %.0f MB streamed per step, BVH %.0f MB "
-                         "(8 octant variants of 64 B nodes at leaf size 2 + 48 B triangles), vs 126 MB L2" % (
-                32e-6 * args.ommatidia * args.samples, 12e-6 * args.ommatidia * args.samples, (256 + 48) * 1e-6 * args.triangles)}
+            "l2_policy": "inputs larger than L2: RNG state %.0f MB streamed per launch, BVH %.0f MB (8 octant variants of 64 B "
+                         "nodes at leaf size 2 + 48 B triangles), vs 126 MB L2; a new camera pose every frame" % (
+                32e-6 * args.ommatidia * args.samples, (256 + 48) * 1e-6 * args.triangles)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--repeats", type=int, default=5, help="timed batches of --steps frames; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fused", choices=sorted(MODES))
     ap.add_argument("--triangles", type=int, default=1_000_000)
     ap.add_argument("--ommatidia", type=int, default=10_000)
     ap.add_argument("--samples", type=int, default=1024)
-    ap.add_argument("--ref-rays-per-step", type=float, default=2e6)
+    ap.add_argument("--ref-rays-per-step", type=float, default=4e6)
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: host threads (0 = all)")
+    ap.add_argument("--ref-portable", action="store_true", help="reference arm: time the shipped -O2 checker build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the rays/s of the other render modes")
     ap.add_argument("--sweep", action="store_true", help="also report rays/s for S in {1,32,64,256}")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -280,7 +343,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -294,134 +357,184 @@ def main():
     lib.loadGlTFscene(gltf.encode())
     if not lib.gotoCameraByName(b"compound-cam"):
         raise SystemExit("compound-cam not found")
-    N, S, K, W = args.ommatidia, args.samples, args.steps, args.warmup
+    N, S, K, W, R = args.ommatidia, args.samples, args.steps, args.warmup, max(1, args.repeats)
     assert lib.getCurrentEyeOmmatidialCount() == N
     lib.setCurrentEyeShaderName(b"single_dimension_fast")
     er.setRenderSize(lib, N, 1)
+    lib.crSetRenderMode(*MODES[args.mode])
     lib.setCurrentEyeSamplesPerOmmatidium(S)
     pose0 = np.zeros(12, np.float32)
     lib.crDebugCopyCameraPose(pose0.ctypes.data)
     cam_pos, axes = pose0[:3].copy(), pose0[3:].copy()
+    rays_per_step = N * S
 
-    # rank r renders global frames [r*(W+K), (r+1)*(W+K)): its streams start at that frame
-    first = rank * (W + K)
+    # rank r renders global frames [r*span, (r+1)*span): its streams start at that frame
+    span = W + (R + 1) * K
+    first = rank * span
     lib.crSetFirstFrame(first)
-    launches0 = lib.crGetLaunchCount()
 
-    # ------------------------------------------------------------------ device-resident value
+    send = gathered = None
     out_dev = None
     if world > 1:
-        import torch
         send = torch.empty((K, N, 4), dtype=torch.uint8, device="cuda")
         gathered = torch.empty((world * K, N, 4), dtype=torch.uint8, device="cuda")
         out_dev = send.data_ptr()
+        torch.cuda.synchronize()                          # the renderer writes `send` from its own (non-blocking) stream
     sampler = ClockSampler(local)
-    sampler.start()                                     # sampled from warm-up to the end of the e2e loop
-    warm = poses_for(cam_pos, axes, W, first)
-    er.renderPoseBatch(lib, warm)                       # W untimed warm-up frames (incl. RNG init)
-    timed = poses_for(cam_pos, axes, K, first + W)
-    if world > 1:
-        dist.barrier()
+    sampler.start()                                       # sampled from warm-up to the end of the e2e loop
+
+    def timed_batches(first_frame, repeats, with_gather=True):
+        """`repeats` batches of K frames; per batch: barrier + sync, CUDA events around the fused launches on the library
+        stream (+ torch events around ncclAllGather), max over ranks."""
+        out = []
+        for b in range(repeats):
+            timed = poses_for(cam_pos, axes, K, first_frame + b * K)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+                er.renderPoseBatch(lib, timed, out_device_ptr=out_dev)       # returns after the stream is idle
+                dev_ms = lib.crGetLastTraceMs()
+                if with_gather:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
+                    e1.record()
+                    torch.cuda.synchronize()
+                    dev_ms += e0.elapsed_time(e1)
+                t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dev_ms = float(t.item())
+            else:
+                er.renderPoseBatch(lib, timed)                                # D2H of K*N*4 bytes happens AFTER the event pair
+                dev_ms = lib.crGetLastTraceMs()
+            out.append(dev_ms)
+        return out
+
+    er.renderPoseBatch(lib, poses_for(cam_pos, axes, W, first), out_device_ptr=None)   # W untimed warm-up frames (incl. RNG init)
+    if world > 1:                                         # ... and the collective with its real shape (first call builds channels)
+        er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, first + W), out_device_ptr=out_dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
         torch.cuda.synchronize()
-    launches1 = lib.crGetLaunchCount()
-    if world > 1:
-        _, host_ms = er.renderPoseBatch(lib, timed, out_device_ptr=out_dev)
-        dev_ms = lib.crGetLastTraceMs()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
-        e1.record()
-        torch.cuda.synchronize()
-        dev_ms += e0.elapsed_time(e1)
-        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-        dist.barrier()
     else:
-        out_host, host_ms = er.renderPoseBatch(lib, timed)      # D2H of K*N*4 bytes happens AFTER the event pair
-        dev_ms = lib.crGetLastTraceMs()
+        er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, first + W))      # same shape as the timed batches (allocations)
+    launches1 = lib.crGetLaunchCount()
+    batch_ms = timed_batches(first + W + K, R)
     launches_timed = lib.crGetLaunchCount() - launches1
-    lib.crGetLastBatchFrames.restype = C.c_int
-    frames_per_launch = lib.crGetLastBatchFrames()
-    rays_per_step = N * S
+    frames_per_launch = int(lib.crGetLastBatchFrames())
+    dev_ms = float(np.median(batch_ms))
     value = world * K * rays_per_step / (dev_ms * 1e-3)
 
     # ------------------------------------------------------------------ e2e through the reference-facing C ABI
     # every rank drives its own GPU through the per-frame API at the same time: host pose in, host frame out
+    def e2e_run(frames, first_frame):
+        for _ in range(2):
+            lib.setCameraPosition(float(cam_pos[0]), float(cam_pos[1] + 0.5), float(cam_pos[2]))
+            lib.renderFrame(); lib.getFramePointer()
+        pe = poses_for(cam_pos, axes, frames, first_frame)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        checksum = 0
+        for k in range(frames):
+            lib.setCameraPosition(float(pe[k, 0]), float(pe[k, 1]), float(pe[k, 2]))       # host pose in
+            lib.renderFrame()
+            fr = lib.getFramePointer()                                                       # D2H of the frame
+            checksum += int(fr[0, 0, 0])
+        s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s = float(t.item())
+        return s
     Ke = K
-    for k in range(2):
-        lib.setCameraPosition(float(cam_pos[0]), float(cam_pos[1] + 0.5), float(cam_pos[2]))
-        lib.renderFrame(); lib.getFramePointer()
-    pe = poses_for(cam_pos, axes, Ke, first + W + K)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    checksum = 0
-    for k in range(Ke):
-        lib.setCameraPosition(float(pe[k, 0]), float(pe[k, 1]), float(pe[k, 2]))       # host pose in
-        lib.renderFrame()
-        fr = lib.getFramePointer()                                                       # D2H of the frame
-        checksum += int(fr[0, 0, 0])
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = e2e_run(Ke, first + W + (R + 1) * K)
+
+    # ------------------------------------------------------------------ the other render modes (one GPU only)
+    modes = None
+    if world == 1 and not args.no_modes:
+        modes = {args.mode: {"rays_per_sec": value, "e2e_rays_per_sec": Ke * rays_per_step / e2e_s}}
+        for name in ("ordered", "fused", "fused_fast"):
+            if name in modes:
+                continue
+            lib.crSetRenderMode(*MODES[name])
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, 0))
+            ms = float(np.median(timed_batches(K, 3)))
+            es = e2e_run(Ke, 4 * K)
+            modes[name] = {"rays_per_sec": K * rays_per_step / (ms * 1e-3), "e2e_rays_per_sec": Ke * rays_per_step / es,
+                           "frames_per_launch": int(lib.crGetLastBatchFrames())}
+        modes["note"] = ("ordered = reference's sequential per-sample sum + cr_math (bit-exact vs the checker); fused = in-kernel "
+                         "reduction in a fixed order the checker restates (same rays, hits, colours); fused_fast = fused + "
+                         "hardware sin/cos/log/pow as the reference's --use_fast_math build (tolerance 1/255)")
+        lib.crSetRenderMode(*MODES[args.mode])
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
     clocks = sampler.stop()
 
     out = None
     if rank == 0:
         e2e = {"value": world * Ke * rays_per_step / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 4 * N,
                "ms_per_step": 1e3 * e2e_s / Ke, "api": "setCameraPosition + renderFrame + getFramePointer (ctypes), every rank "
-               "concurrently on its own GPU; max over ranks"}
+               "concurrently on its own GPU; max over ranks", "mode": args.mode}
 
-        # -------------------------------------------------------------- roofline of the dominant kernel (K1)
+        # -------------------------------------------------------------- rooflines of the dominant kernel (K1)
         tc = traversal_counters(lib, er)
-        n_node, n_tri, hit_frac = tc["nodes"], tc["tris"], tc["hit_fraction"]
-        lib.crGetLastBatchFrames.restype = C.c_int
-        F = max(1, int(frames_per_launch))
-        # per ray: node + triangle fetches, RNG state read+write once per F-frame launch, 12 B sample write +
-        # 12 B read by the ordered sum, ommatidium row + result amortised over S
-        bytes_per_ray = 64.0 * n_node + 48.0 * n_tri + 64.0 / F + 24.0 + 48.0 / S
+        n_node, n_tri = tc["nodes"], tc["tris"]
+        F = max(1, frames_per_launch)
+        # SURVEY 8(d), strictly: per ray 64 B per BVH node fetched + 48 B per triangle tested + RNG state (32 B read + 32 B
+        # written once per F-frame launch) + ommatidium row (32 B) and result (16 B) amortised over S
+        bytes_per_ray = 64.0 * n_node + 48.0 * n_tri + 64.0 / F + 48.0 / S
         peak, peak_src = measured_peak_gbs()
-        achieved = (value / world) * bytes_per_ray / 1e9
-        traffic = None
-        tj = {}
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                traffic = tj.get("dram_bytes_per_launch") if tj.get("frames_per_launch") == F else None
-            except Exception:
-                traffic, tj = None, {}
-        dram_gbs = (traffic / (dev_ms / K * F * 1e-3) / 1e9) if traffic else None # measured DRAM bytes (ncu) over the live launch time
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "dram_achieved_gbs": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
-                    "kernel": "k_traceCompound<false,true>", "frames_per_launch": F,
-                    "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_step * F, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
-                    "nodes_per_ray_from_root": tc["nodes_from_root"], "tris_per_ray_from_root": tc["tris_from_root"],
-                    "hit_fraction": hit_frac, "peak_source": peak_src,
-                    "note": "achieved = SURVEY 8(d) algorithmic bytes (64*nodes + 48*tris + 64/F RNG r+w + 24 sample w+r + 48/S per ray) / time, "
-                            "with nodes/tris per ray counted on the device by the dump variant of the kernel (entry frontier active; "
-                            "*_from_root = what a root-to-leaf walk of the same tree fetches; the per-ommatidium frontier pass adds < 0.1 B/ray). "
-                            "The BVH bytes are L1/L2 hits (one viewpoint per frame): the kernel is issue/latency-bound, not HBM-bound. "
-                            "dram_* = ncu-measured DRAM bytes per launch (RNG state + samples) / live launch time: the true HBM "
-                            "utilisation -- see profiles/ for the ncu summaries"}
-        roofline["issue"] = issue_roofline(tj, F, rays_per_step, value / world, clocks.get("sm_mhz"))
-        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(gltf, S)
+        rate = value / world                                            # rays/s per GPU
+        launch_s = dev_ms * 1e-3 * F / K                                # average duration of one F-frame launch group, live
+        nm = ncu_model(args.mode, F)
+        traffic = nm["dram_bytes"] if nm else None
+        hbm = {"bound": "hbm", "achieved": rate * bytes_per_ray / 1e9, "peak": peak, "unit": "GB/s",
+               "frac": rate * bytes_per_ray / 1e9 / peak, "bytes_per_ray": bytes_per_ray,
+               "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_step * F,
+               "dram_achieved_gbs": (traffic / launch_s / 1e9) if traffic else None,
+               "dram_frac": (traffic / launch_s / 1e9 / peak) if traffic else None, "peak_source": peak_src,
+               "note": "SURVEY 8(d) formula: 64*nodes + 48*tris + 64/F (RNG state r+w per launch) + 48/S per ray, nodes/tris counted on "
+                       "the device.  These bytes are L1/L2 hits (one viewpoint per frame): dram_* = ncu-measured DRAM bytes of the "
+                       "launch over its live duration is the true HBM utilisation, and it is small -- the kernel is not HBM-bound"}
+        issue = None
+        if nm and clocks.get("sm_mhz"):
+            per_ray = nm["inst_executed"] / (float(rays_per_step) * F)
+            ipeak = 148 * 4 * float(clocks["sm_mhz"]) * 1e6
+            issue = {"achieved": rate * per_ray / 1e9, "peak": ipeak / 1e9, "unit": "G warp-inst/s", "frac": rate * per_ray / ipeak,
+                     "warp_inst_per_ray": per_ray, "active_lanes_per_inst": nm["thread_inst_per_warp_inst"],
+                     "ncu_issue_active_pct": nm["issue_active_pct"]}
+        roofline = {"bound": "issue", "kernel": KERNEL_OF_MODE[args.mode], "frames_per_launch": F,
+                    "achieved": issue["achieved"] if issue else None, "peak": issue["peak"] if issue else None,
+                    "unit": "G warp-inst/s", "frac": issue["frac"] if issue else None, "traffic": traffic,
+                    "issue": issue, "hbm": hbm, "ncu": nm,
+                    "nodes_per_ray": n_node, "tris_per_ray": n_tri, "nodes_per_ray_from_root": tc["nodes_from_root"],
+                    "tris_per_ray_from_root": tc["tris_from_root"], "hit_fraction": tc["hit_fraction"],
+                    "traversing_fraction": tc["traversing_fraction"], "nodes_per_traversing_ray": tc["nodes_per_traversing_ray"],
+                    "tris_per_traversing_ray": tc["tris_per_traversing_ray"],
+                    "hit_only_rays_per_sec_equivalent": rate * tc["hit_fraction"],
+                    "hit_ids_equal_oracle_walk": tc["hit_ids_equal_oracle_walk"],
+                    "note": "K1 is bound by warp-instruction issue (and the load latency behind it), not by HBM: `achieved` = warp "
+                            "instructions per launch counted by ncu (profiles/k1_traffic.json, same kernel and workload, reconstructed "
+                            "at this run's frames per launch) x live launches/s; `peak` = 148 SMs x 4 schedulers x the SM clock sampled "
+                            "during the run.  `traffic` = ncu DRAM bytes per launch.  `hbm` is the SURVEY 8(d) line.  About half of the "
+                            "eye looks at the sky (hit_fraction): those rays never enter the BVH"}
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args)
         out = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
-               "gpu_launches": int(launches_timed), "roofline": roofline, "cpu_baseline": cpu,
+               "data": "synthetic", "config": dict(workload_config(args), mode=args.mode), "clocks": clocks, "e2e": e2e,
+               "gpu_launches": int(launches_timed), "gpu_launches_per_batch": int(launches_timed) // R,
+               "repeats": R, "batch_ms": batch_ms, "roofline": roofline, "cpu_baseline": cpu, "modes": modes,
                "ommatidia_frames_per_sec": value / S, "bvh_build_ms": lib.crGetBvhBuildMs(),
-               "timing": "CUDA events around the K fused trace+pack launches on the library stream"
-                         + (", plus torch events around ncclAllGather; max over ranks" if world > 1 else "")}
+               "timing": f"median of {R} batches of {K} frames; CUDA events around each batch's fused trace+reduce launches on the "
+                         "library stream" + (", plus torch events around ncclAllGather of the batch's rows; max over ranks per batch"
+                                             if world > 1 else "")}
         if args.sweep:
             sweep = {}
             for s in (1, 32, 64, 256):
                 lib.setCurrentEyeSamplesPerOmmatidium(s)
-                er.renderPoseBatch(lib, warm)
-                er.renderPoseBatch(lib, timed)
+                er.renderPoseBatch(lib, poses_for(cam_pos, axes, W, 0))
+                er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, W))
                 sweep[str(s)] = K * N * s / (lib.crGetLastTraceMs() * 1e-3)
             out["sweep_rays_per_sec_by_S"] = sweep
     if world > 1:

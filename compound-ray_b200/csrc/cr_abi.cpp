@@ -210,6 +210,12 @@ void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex)
     renderer().setOmmatidialShard(globalCount, firstIndex);
     CR_GUARD_END()
 }
+void crSetRenderMode(int fusedReduction, int fastMath)
+{
+    if (fusedReduction >= 0) renderer().fusedReduce = fusedReduction != 0;
+    if (fastMath >= 0) renderer().fastMath = fastMath != 0;
+}
+int crGetRenderMode(void) { return (renderer().fusedReduce ? 1 : 0) | (renderer().fastMath ? 2 : 0); }
 double crGetLastTraceMs(void) { return renderer().lastTraceMs(); }
 unsigned long long crGetLaunchCount(void) { return renderer().launchCount(); }
 double crGetBvhBuildMs(void) { return renderer().bvhBuildMs(); }
@@ -320,6 +326,13 @@ size_t crDebugCopyLastRayCounts(int32_t* counts2)
 {
     CR_GUARD_BEGIN
     return renderer().debugCopyLastRayCounts(counts2);
+    CR_GUARD_END(0)
+}
+void crDebugSetCandidateLists(int on) { renderer().candidateLists = on; }
+size_t crDebugCopyCandidateLists(int32_t* out, size_t records)
+{
+    CR_GUARD_BEGIN
+    return renderer().debugCopyCandidateLists(out, records);
     CR_GUARD_END(0)
 }
 void crDebugSetEntryFrontier(int on, int minSamples, long long minRays)

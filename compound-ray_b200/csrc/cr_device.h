@@ -21,9 +21,12 @@
 //   pre     float4[4*N]        per-ommatidium ray invariants (origin offset, sd, axis, focal, perp, cone bound, perp x axis, perp . axis)
 //   entries int4[F*N]          per (frame, ommatidium): up to 4 BVH subtree roots its sample cone can reach
 //                              (near to far, packed from .x, 0x80000000 = none)
+//   lists   int[F*N][16]       per (frame, ommatidium): candidate list -- [0] = element count n (0..15; -1 = no list, walk the
+//                              frontier), [1..n] = node << 2 | mask of that node's children that are leaves the cone can reach
 //   rng     uint4[2*N*S]       32 B compact XORWOW state per sample stream, laid out [o][s]
 //             r[0] = (d, v0, v1, v2)   r[1] = (v3, v4, boxmuller_flag, boxmuller_extra bits)
-//   samples float[3*N*S]       per-sample colour/S, laid out [o][s] (12 B per ray, written by K1)
+//   samples float[3*N*S]       per-sample colour/S, laid out [o][s] (12 B per ray, written by K1; ordered mode)
+//   partials float4[N*S/32]    fused mode instead: one butterfly sum of 32 samples per warp (0.5 B per ray)
 //   summed  float4[N]          per-ommatidium RGB: sequential sum of the samples (K1b)
 #pragma once
 #include <cuda_runtime.h>
@@ -77,6 +80,10 @@ struct EyeParams {
     uchar4* fastRow = nullptr;           // when set: K1b also writes make_color(summed[i]) for i < fastRowCount
     int fastRowCount = 0;
     const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
+    float4* partials = nullptr;          // fused reduction: [nFrames][N][S/32] per-warp sums of 32 samples (K1 -> k_sumPartials)
+    const int* lists = nullptr;          // [nFrames][N][16] candidate lists (k_buildEntries stage 2): header = element count, -1 = none
+    bool fused = false;                  // in-kernel reduction (needs S % 32 == 0) instead of the ordered per-sample buffer
+    bool fast = false;                   // hardware elementary functions instead of cr_math.h
     DevicePose pose;
 };
 
@@ -108,13 +115,14 @@ enum Projection : int {
 void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, unsigned long long nGlobal, unsigned long long oFirst,
                    const uint4* jumpTable, cudaStream_t stream);
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream);
-void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream);
+void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, int* lists, cudaStream_t stream);
+int candidateListStride();    // ints per (frame, ommatidium) record of the candidate lists
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);
-void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
-void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchProjectVector(int mode, bool fast, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchProjectRaw(bool fast, const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream);
-void launchProjectMap(bool ids, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream);
-void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame,
+void launchProjectMap(bool ids, bool fast, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream);
+void launchCamera(const DeviceScene& sc, int kind, bool fast, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame,
                   int W, int H, cudaStream_t stream);
 void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,
                      cudaStream_t stream);

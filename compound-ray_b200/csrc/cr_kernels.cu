@@ -47,6 +47,27 @@ __device__ __forceinline__ V3 fcross(V3 a, V3 b)
 { return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))); }
 
 // ------------------------------------------------------------------------------------------
+// Elementary-function policy.  FAST = false: the specified binary32 algorithms of cr_math.h (every bit
+// reproducible by the CPU checker).  FAST = true (opt-in, crSetRenderMode): the hardware approximations the
+// reference itself runs -- its device code is built with --use_fast_math (CMakeLists.txt:142) and cuRAND's
+// Box-Muller calls __sincosf (curand_normal.h:70-87) -- MUFU sin/cos/lg2/ex2 instead of ~30-instruction
+// polynomials.  Rays then differ from the exact mode in the last bits, so this mode is held to the
+// north_star tolerance (max |dRGB| <= 1/255, mean <= 1e-4), not to bit-exactness.
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+struct Fn {
+    static __device__ __forceinline__ void sincos(float x, float& s, float& c)
+    {
+        if (FAST) __sincosf(x, &s, &c);
+        else crm::sincos(x, s, c);
+    }
+    static __device__ __forceinline__ float log(float x) { return FAST ? __logf(x) : crm::log(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return FAST ? __powf(x, y) : crm::pow(x, y); }
+    static __device__ __forceinline__ float asin(float x) { return FAST ? asinf(x) : crm::asin(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return FAST ? atan2f(y, x) : crm::atan2(y, x); }
+};
+
+// ------------------------------------------------------------------------------------------
 // cuRAND XORWOW on a 32-byte compact state (curand_kernel.h:150-156, :863-874;
 // curand_normal.h:70-87,313-326; curand_uniform.h:69-72).  Streams/seeds as in shaders.cu:680-695.
 // ------------------------------------------------------------------------------------------
@@ -83,6 +104,7 @@ __device__ __forceinline__ float rngUniform(Rng& r)
     const uint32_t x = rngNext(r);
     return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
+template <bool FAST = false>
 __device__ __forceinline__ float rngNormal(Rng& r)
 {
     if (r.flag != 1) {
@@ -90,9 +112,9 @@ __device__ __forceinline__ float rngNormal(Rng& r)
         const uint32_t y = rngNext(r);
         const float u = (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
         const float v = (float)y * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2.0f);
-        const float s = sqrtf(-2.0f * crm::log(u));
+        const float s = sqrtf(-2.0f * Fn<FAST>::log(u));
         float sn, cs;
-        crm::sincos(v, sn, cs);
+        Fn<FAST>::sincos(v, sn, cs);
         r.extra = cs * s;
         r.flag = 1;
         return sn * s;
@@ -172,10 +194,11 @@ __global__ void k_rngInit(uint4* __restrict__ rng, int N, int S, unsigned long l
 #endif
 constexpr float kConeSigmas = CR_CONE_SIGMAS;   // sample rays with |splay| <= kConeSigmas*sd start from the entry frontier
 
+template <bool FAST = false>
 __device__ __forceinline__ V3 rotatePoint(V3 p, float angle, V3 axis)   // axis NOT re-normalised
 {
     float sn, cs;
-    crm::sincos(angle, sn, cs);
+    Fn<FAST>::sincos(angle, sn, cs);
     const V3 a = vmuls(p, cs);
     const V3 b = vmuls(vcross(axis, p), sn);
     const V3 c = vmuls(axis, (1.0f - cs) * vdot(axis, p));
@@ -210,20 +233,21 @@ __global__ void k_prepOmmatidia(const float4* __restrict__ omm, int N, float4* _
     pre[kPreStride * o + 3] = make_float4(pxa.x, pxa.y, pxa.z, pda);
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ Ray ommatidialRay(const float4 p0, const float4 p1, const float4 p2, const float4 p3, const DevicePose& P,
                                              Rng& rng, float& splayOut)
 {
     const V3 rp = mk(p0.x, p0.y, p0.z);
     const V3 axis = mk(p1.x, p1.y, p1.z);
     const V3 perp = mk(p2.x, p2.y, p2.z);
-    const float splay = rngNormal(rng) * p0.w;
+    const float splay = rngNormal<FAST>(rng) * p0.w;
     splayOut = splay;
     const float axisAngle = rngUniform(rng) * crm::kPi;
     // = rotatePoint(axis, splay, perp) with cross(perp, axis) and dot(perp, axis) taken from the table
     float sSn, sCs;
-    crm::sincos(splay, sSn, sCs);
+    Fn<FAST>::sincos(splay, sSn, sCs);
     const V3 splayed = vadd(vadd(vmuls(axis, sCs), vmuls(mk(p3.x, p3.y, p3.z), sSn)), vmuls(perp, (1.0f - sCs) * p3.w));
-    const V3 rd = rotatePoint(splayed, axisAngle, axis);
+    const V3 rd = rotatePoint<FAST>(splayed, axisAngle, axis);
     const V3 X = mk(P.xx, P.xy, P.xz), Y = mk(P.yx, P.yy, P.yz), Z = mk(P.zx, P.zy, P.zz);
     Ray r;
     r.o = vadd(vadd(vadd(mk(P.px, P.py, P.pz), vmuls(X, rp.x)), vmuls(Y, rp.y)), vmuls(Z, rp.z));
@@ -425,12 +449,88 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
 }
 
 // ------------------------------------------------------------------------------------------
+// Closest hit through an ommatidium's CANDIDATE LIST (k_buildEntries, second stage).  The sample cone of most
+// ommatidia reaches only a handful of BVH leaves; for those the frontier pass flattens the part of the tree the
+// cone can reach into a short list of "pre-leaf" elements (node index, which of its two children are reachable
+// leaves).  The 32 lanes of a warp -- 32 samples of that ommatidium -- then run
+//   phase 1, in lockstep over the list (no stack, no divergence, one node address per octant variant for the whole
+//            warp): each lane tests its own ray against the listed child boxes and notes the leaves it hits as bits;
+//   phase 2, per lane: each lane walks ITS bits and tests the triangles of ITS leaves -- different triangles in
+//            different lanes under the same instructions.
+// The per-lane stack walk below the frontier, whose lanes drift out of phase (14.7 of 32 lanes live in its node loop,
+// 8.5 on its stack: profiles/r01e_final_k1_ncu_summary.txt), is gone for these warps.  A lane tests every listed leaf
+// whose box its ray passes, i.e. a superset of the leaves the stack walk would test (which also prunes by the
+// closest hit so far) -- and with the lowest-primitive tie rule the closest hit, hence every output bit, is the same.
+// Must be called by all 32 lanes of the warp; `list` is warp-uniform.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kListMax = 15;                 // elements per (frame, ommatidium); the record is 1 + kListMax ints = 64 B
+constexpr int kListStride = kListMax + 1;
+constexpr int kListFallback = -1;            // header value: no list -- walk the entry frontier per lane
+static_assert(2 * kListMax <= 32, "two bits per element in the per-lane hit mask");
+static_assert(kSmemStack >= 1, "the warp's leaf refs live in row 0 of the shared stack");
+
+template <bool COUNT>
+__device__ __forceinline__ Hit traceList(const float4* __restrict__ nodesAll, size_t variantStride, const float4* __restrict__ tris,
+                                         const Ray& ray, const float tmax, int* sWarp, const int lane, int* nodeCount, int* triCount,
+                                         const int* __restrict__ list, const int n)
+{
+    Hit best;
+    best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+    if (n == 0) {                                                  // the cone reaches no leaf: every sample misses
+        if (COUNT) { *nodeCount = 0; *triCount = 0; }
+        return best;
+    }
+    RayBox rb;
+    int sx, sy, sz;
+    setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
+    setupAxis(ray.o.y, ray.d.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
+    setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
+    const float4* __restrict__ nodes = nodesAll + (size_t)(sx | (sy << 1) | (sz << 2)) * variantStride;
+    unsigned bits = 0u;
+    __syncwarp();                                                   // the previous frame's phase 2 is done with the refs
+    for (int e = 0; e < n; e++) {
+        const int w = __ldg(list + 1 + e);                          // node << 2 | reachable-leaf mask of its two children
+        const float4* np = nodes + 4 * (size_t)(w >> 2);
+        float4 n0, n1, n2, n3;
+        ldgNode(np, n0, n1, n2, n3);
+        const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), ray.tmin));
+        const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), tmax));
+        const float tn1 = fmax3(fmaf(n1.x, rb.nix, rb.nax), fmaf(n1.z, rb.niy, rb.nay), fmaxf(fmaf(n2.z, rb.niz, rb.naz), ray.tmin));
+        const float tf1 = fmin3(fmaf(n1.y, rb.fix, rb.fax), fmaf(n1.w, rb.fiy, rb.fay), fminf(fmaf(n2.w, rb.fiz, rb.faz), tmax));
+        const unsigned h0 = ((w & 1) != 0 && tn0 <= tf0) ? 1u : 0u, h1 = ((w & 2) != 0 && tn1 <= tf1) ? 2u : 0u;
+        bits |= (h0 | h1) << (2 * e);
+        if (lane == 0) *reinterpret_cast<int2*>(sWarp + 2 * e) = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
+    }
+    __syncwarp();
+    int tc = 0;
+    while (bits != 0u) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1u;
+        const int x = ~sWarp[b];                                    // leaf ref of (element b >> 1, child b & 1)
+        const int first = x >> 3, cnt = (x & 7) + 1;
+        for (int k = 0; k < cnt; k++) {
+            float t, u, v;
+            int prim;
+            if (COUNT) tc++;
+            if (triTest(tris + 3 * (size_t)(first + k), ray.o, ray.d, ray.tmin, best.t, t, u, v, prim)) {
+                if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
+            }
+        }
+    }
+    if (COUNT) { *nodeCount = n; *triCount = tc; }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
 // Shading: closest hit (shaders.cu:779-811 live part; cuda/LocalGeometry.h:55-156) and the two
 // miss programs (shaders.cu:740-756).  params.lighting is hard-wired false in the reference
 // (libEyeRenderer.cpp:98), so the result is the base colour.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ V3 linearize(V3 c) { return mk(crm::pow(c.x, 2.2f), crm::pow(c.y, 2.2f), crm::pow(c.z, 2.2f)); }
+template <bool FAST = false>
+__device__ __forceinline__ V3 linearize(V3 c) { return mk(Fn<FAST>::pow(c.x, 2.2f), Fn<FAST>::pow(c.y, 2.2f), Fn<FAST>::pow(c.z, 2.2f)); }
 
+template <bool FAST = false>
 __device__ __forceinline__ V3 shadeHit(const DeviceScene& sc, const Hit& h)
 {
     const uint4 pr = __ldg(sc.prims + h.prim);
@@ -440,7 +540,7 @@ __device__ __forceinline__ V3 shadeHit(const DeviceScene& sc, const Hit& h)
         const float4 c0 = __ldg(sc.colors + pr.x), c1 = __ldg(sc.colors + pr.y), c2 = __ldg(sc.colors + pr.z);
         const V3 col = mk(w0 * c0.x + h.u * c1.x + h.v * c2.x, w0 * c0.y + h.u * c1.y + h.v * c2.y,
                           w0 * c0.z + h.u * c1.z + h.v * c2.z);
-        return linearize(col);
+        return linearize<FAST>(col);
     }
     if (m->hasTex) {
         float uu = h.u, vv = h.v;                                     // LocalGeometry.h:97-103
@@ -450,16 +550,17 @@ __device__ __forceinline__ V3 shadeHit(const DeviceScene& sc, const Hit& h)
             vv = w0 * t0.y + h.u * t1.y + h.v * t2.y;
         }
         const float4 tx = tex2D<float4>((cudaTextureObject_t)m->tex, uu, vv);
-        return linearize(mk(tx.x, tx.y, tx.z));
+        return linearize<FAST>(mk(tx.x, tx.y, tx.z));
     }
     return mk(m->baseColor[0], m->baseColor[1], m->baseColor[2]);
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ V3 shadeMiss(int shader, V3 rayDir)
 {
     const V3 dir = vnormalize(rayDir);
     if (shader == 1) {                                                // __miss__simple_sky
-        const float mix = fminf(fmaxf(0.0f, (crm::asin(dir.y) * 2.0f) / crm::kPi), 1.0f);
+        const float mix = fminf(fmaxf(0.0f, (Fn<FAST>::asin(dir.y) * 2.0f) / crm::kPi), 1.0f);
         const float i255 = 1.0f / 255.0f;                             // sutil float3/float = * reciprocal
         const V3 upper = mk(1.0f * i255, 31.0f * i255, 117.0f * i255);
         const V3 lower = mk((143.0f * i255) * 0.8f, (179.0f * i255) * 0.8f, (203.0f * i255) * 0.8f);
@@ -467,16 +568,19 @@ __device__ __forceinline__ V3 shadeMiss(int shader, V3 rayDir)
     }
     const float border = 0.01f;                                       // __miss__default_background
     if (fabsf(dir.x) < border || fabsf(dir.y) < border || fabsf(dir.z) < border) return mk(0.0f, 0.0f, 0.0f);
-    return mk((crm::atan2(dir.z, dir.x) + crm::kPi) / (crm::kPi * 2.0f), (crm::asin(dir.y) + crm::kPi / 2.0f) / crm::kPi, 0.0f);
+    return mk((Fn<FAST>::atan2(dir.z, dir.x) + crm::kPi) / (crm::kPi * 2.0f), (Fn<FAST>::asin(dir.y) + crm::kPi / 2.0f) / crm::kPi, 0.0f);
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ uchar4 makeColor(float r, float g, float b)   // shaders.cu:180-189
 {
     constexpr float ex = static_cast<float>(1.0 / static_cast<double>(2.2f));
-    return make_uchar4(static_cast<unsigned char>(crm::pow(fminf(fmaxf(r, 0.0f), 1.0f), ex) * 255.0f),
-                       static_cast<unsigned char>(crm::pow(fminf(fmaxf(g, 0.0f), 1.0f), ex) * 255.0f),
-                       static_cast<unsigned char>(crm::pow(fminf(fmaxf(b, 0.0f), 1.0f), ex) * 255.0f), 255u);
+    return make_uchar4(static_cast<unsigned char>(Fn<FAST>::pow(fminf(fmaxf(r, 0.0f), 1.0f), ex) * 255.0f),
+                       static_cast<unsigned char>(Fn<FAST>::pow(fminf(fmaxf(g, 0.0f), 1.0f), ex) * 255.0f),
+                       static_cast<unsigned char>(Fn<FAST>::pow(fminf(fmaxf(b, 0.0f), 1.0f), ex) * 255.0f), 255u);
 }
+__device__ __forceinline__ uchar4 makeColorMode(bool fast, float r, float g, float b)
+{ return fast ? makeColor<true>(r, g, b) : makeColor<false>(r, g, b); }
 
 // ------------------------------------------------------------------------------------------
 // K0b.  Entry frontier.  All sample rays of one ommatidium leave ONE origin inside a narrow cone
@@ -537,7 +641,8 @@ __device__ __forceinline__ void entryAppend(EntryList& L, int ref, float key, bo
     L.n++;
 }
 
-__global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, const EyeParams ep, int4* __restrict__ entries)
+__global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, const EyeParams ep, int4* __restrict__ entries,
+                                                      int* __restrict__ lists)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long idx = tid / kEntryK;
@@ -630,16 +735,69 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     };
     cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
     entries[idx] = make_int4(L.ref[0], L.ref[1], L.ref[2], L.ref[3]);
+    if (lists == nullptr) return;
+
+    // Stage 2: candidate list.  Depth-first from the frontier with the same cone test, flattening what the cone can
+    // reach into "pre-leaf" elements (node << 2 | mask of its children that are reachable LEAVES); reachable internal
+    // children are descended into, nearer child first, so the list runs roughly near to far.  The walk gives up --
+    // header kListFallback, K1 then walks the frontier per lane -- as soon as the cone turns out to reach more than
+    // kListMax elements, after kListVisits nodes, or when the frontier itself was a fallback (ok == false).
+    // Header 0 = the cone reaches no leaf at all (sky): K1 skips traversal.
+    int* out = lists + (size_t)idx * kListStride;
+    constexpr int kListVisits = 48, kListStack = 16;
+    int stack[kListStack];
+    int sp = 0, n = 0, visits = 0;
+    bool good = ok;
+#pragma unroll
+    for (int k = kEntryK - 1; k >= 0; k--)
+        if (k < L.n) stack[sp++] = L.ref[k];                      // nearest entry on top
+    while (sp > 0 && good) {
+        const int node = stack[--sp];
+        if (++visits > kListVisits) { good = false; break; }
+        const float4* np = sc.nodes + 4 * (size_t)node;             // octant variant 0 = (min, max)
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+        const V3 min0 = mk(n0.x, n0.z, n2.x), max0 = mk(n0.y, n0.w, n2.y);
+        const V3 min1 = mk(n1.x, n1.z, n2.z), max1 = mk(n1.y, n1.w, n2.w);
+        const bool h0 = coneMayTouchBox(C, min0, max0), h1 = coneMayTouchBox(C, min1, max1);
+        const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+        const int mask = ((h0 && r0 < 0) ? 1 : 0) | ((h1 && r1 < 0) ? 2 : 0);
+        if (mask) {
+            if (n == kListMax) { good = false; break; }
+            out[1 + n] = (node << 2) | mask;
+            n++;
+        }
+        const bool d0 = h0 && r0 >= 0, d1 = h1 && r1 >= 0;
+        if (d0 && d1) {
+            if (sp + 2 > kListStack) { good = false; break; }
+            const float k0 = vdot(C.axis, vsub(vmuls(vadd(min0, max0), 0.5f), C.apex));
+            const float k1 = vdot(C.axis, vsub(vmuls(vadd(min1, max1), 0.5f), C.apex));
+            const bool near0 = k0 <= k1;
+            stack[sp++] = near0 ? r1 : r0;
+            stack[sp++] = near0 ? r0 : r1;
+        } else if (d0 || d1) {
+            if (sp + 1 > kListStack) { good = false; break; }
+            stack[sp++] = d0 ? r0 : r1;
+        }
+    }
+    out[0] = good ? n : kListFallback;
 }
 
 // ------------------------------------------------------------------------------------------
 // K1.  Persistent warps; work unit = 32 consecutive sample rays r = o*S + s (lanes hold
 // consecutive samples of one ommatidium -> coherent rays, one coalesced 1 KB RNG-state read and
-// one coalesced 384 B colour write per warp).  No block-level synchronisation: per-sample
-// colour/S (shaders.cu:730) goes to the [o][s] sample buffer and K1b sums it IN SAMPLE ORDER,
-// which is exactly the reference's sequential fp32 sum (getSummedOmmatidiumData, shaders.cu:341-347).
+// one coalesced 384 B colour write per warp).  No block-level synchronisation.
+//   FUSED = false: per-sample colour/S (shaders.cu:730) goes to the [o][s] sample buffer and K1b sums it IN SAMPLE
+//                  ORDER, which is exactly the reference's sequential fp32 sum (getSummedOmmatidiumData, :341-347).
+//   FUSED = true : (S % 32 == 0) the 32 samples of the warp are summed here by a shuffle butterfly and lane 0 writes
+//                  ONE float4 partial per warp and frame to partials[f][o][s/32]; k_sumPartials adds the S/32
+//                  partials of a row in a fixed order.  12 B/ray of sample traffic (written here, read back by K1b:
+//                  ~85 % of this path's DRAM bytes) become 0.5 B/ray.  The order of the additions differs from the
+//                  reference's, so the float RGB agrees to rounding (~1e-7 relative), not bit for bit; it is a
+//                  FIXED order, restated by the checker (oracle.fused_sum), so the mode is still reproducible.
+// Traversal: warps whose 32 lanes are samples of one ommatidium with a candidate list (k_buildEntries, stage 2) test
+// that list (traceList); everything else walks the BVH per lane from the entry frontier or the root (traceClosest).
 // ------------------------------------------------------------------------------------------
-template <bool DUMP, bool MULTI>
+template <bool DUMP, bool MULTI, bool FUSED, bool FAST>
 __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCompound(const DeviceScene sc, const EyeParams ep)
 {
     __shared__ int sStack[kSmemStack][kTraceThreads];
@@ -648,6 +806,10 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     const float invS = 1.0f / (float)(uint32_t)ep.S;
     const unsigned stride = gridDim.x * kTraceThreads;
     const int F = MULTI ? ep.nFrames : 1;
+    const int lane = (int)(threadIdx.x & 31u);
+    int* sWarp = &sStack[0][threadIdx.x & ~31u];
+    // S % 32 == 0: the 32 rays of a warp are samples of ONE ommatidium (and `r < total` is warp-uniform)
+    const bool warpRows = (ep.S & 31) == 0;
     for (unsigned r = blockIdx.x * kTraceThreads + threadIdx.x; r < total; r += stride) {
         if (r + stride < total) {                       // warm L2 with the next ray's RNG state
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * (size_t)(r + stride)));
@@ -666,12 +828,11 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 pose.xy = b.x; pose.xz = b.y; pose.yx = b.z; pose.yy = b.w;
                 pose.yz = c.x; pose.zx = c.y; pose.zy = c.z; pose.zz = c.w;
             }
-            const float4* pp4 = ep.pre + kPreStride * (size_t)o;
+            const float4* pp4 = ep.pre + kPreStride * (size_t)o;        // (re-read per frame: L1 hits, no registers held across the walk)
             const float4 p0 = __ldg(pp4), p1 = __ldg(pp4 + 1), p2 = __ldg(pp4 + 2), p3 = __ldg(pp4 + 3);
             float splay;
-            const Ray ray = ommatidialRay(p0, p1, p2, p3, pose, rng, splay);
-            int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
-            if (ep.entries != nullptr && fabsf(splay) <= p2.w) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+            const Ray ray = ommatidialRay<FAST>(p0, p1, p2, p3, pose, rng, splay);
+            const bool inCone = fabsf(splay) <= p2.w;
             if (MULTI) {   // park the state in shared memory: its 8 registers are dead while the ray is traced
                 sRng[0][threadIdx.x] = make_uint4(rng.d, rng.v0, rng.v1, rng.v2);
                 sRng[1][threadIdx.x] = make_uint4(rng.v3, rng.v4, (uint32_t)rng.flag, __float_as_uint(rng.extra));
@@ -679,11 +840,42 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 rngStore(statePtr, rng);
             }
             int nNode = 0, nTri = 0;
-            const Hit h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x],
-                                             kTraceThreads, &nNode, &nTri, entry);
-            const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
-            float* dst = ep.samples + 3 * ((size_t)f * total + r);
-            __stcs(dst, col.x * invS); __stcs(dst + 1, col.y * invS); __stcs(dst + 2, col.z * invS);   // shaders.cu:730
+            Hit h;
+            // Candidate list of this (frame, ommatidium): used when the warp is 32 samples of that ommatidium and every
+            // one of them fell inside the kConeSigmas cone the list was built for (else: the per-lane walk below).
+            const int* list = nullptr;
+            int listN = kListFallback;
+            if (warpRows && ep.lists != nullptr) {
+                list = ep.lists + ((size_t)f * (unsigned)ep.N + o) * kListStride;
+                listN = __ldg(list);
+                if (listN != kListFallback && !__all_sync(kFullMask, inCone)) listN = kListFallback;
+            }
+            if (listN != kListFallback) {
+                h = traceList<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, sWarp, lane, &nNode, &nTri, list, listN);
+            } else {
+                int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
+                if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+                h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
+                                       &nNode, &nTri, entry);
+            }
+            const V3 col = (h.prim >= 0) ? shadeHit<FAST>(sc, h) : shadeMiss<FAST>(sc.missShader, ray.d);
+            float cx = col.x * invS, cy = col.y * invS, cz = col.z * invS;                       // shaders.cu:730
+            if (FUSED) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {        // butterfly: level d adds lane i and lane i^d; all lanes end with the same sum
+                    cx += __shfl_xor_sync(kFullMask, cx, d);
+                    cy += __shfl_xor_sync(kFullMask, cy, d);
+                    cz += __shfl_xor_sync(kFullMask, cz, d);
+                }
+                if (lane == 0) {
+                    const unsigned blocksPerRow = (unsigned)ep.S >> 5;
+                    const unsigned blk = (r - o * (unsigned)ep.S) >> 5;
+                    __stcs(ep.partials + ((size_t)f * (unsigned)ep.N + o) * blocksPerRow + blk, make_float4(cx, cy, cz, 0.0f));
+                }
+            } else {
+                float* dst = ep.samples + 3 * ((size_t)f * total + r);
+                __stcs(dst, cx); __stcs(dst + 1, cy); __stcs(dst + 2, cz);
+            }
             if (MULTI) {
                 const uint4 a = sRng[0][threadIdx.x], b = sRng[1][threadIdx.x];
                 rng.d = a.x; rng.v0 = a.y; rng.v1 = a.z; rng.v2 = a.w; rng.v3 = b.x; rng.v4 = b.y;
@@ -699,6 +891,34 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
             }
         }
         if (MULTI) rngStore(statePtr, rng);
+    }
+}
+
+// K1b of the fused mode: summed[f][o] = fixed-order sum of the S/32 warp partials of the row, one warp per row.
+// Lane l first adds partials l, l+32, l+64, ... in ascending order, then the same butterfly as in K1 combines the 32
+// lanes (S <= 1024: one partial per lane).  Also writes the 8-bit row of single_dimension_fast / pose batches.
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_sumPartials(const float4* __restrict__ partials, int NF, int blocksPerRow, float4* __restrict__ summed,
+                                                     uchar4* __restrict__ fastRow, int fastRowCount)
+{
+    const int row = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
+    const int lane = (int)(threadIdx.x & 31u);
+    if (row >= NF) return;                                   // warp-uniform
+    const float4* p = partials + (size_t)row * blocksPerRow;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (int k = lane; k < blocksPerRow; k += 32) {
+        const float4 q = __ldcs(p + k);
+        cx += q.x; cy += q.y; cz += q.z;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cx += __shfl_xor_sync(kFullMask, cx, d);
+        cy += __shfl_xor_sync(kFullMask, cy, d);
+        cz += __shfl_xor_sync(kFullMask, cz, d);
+    }
+    if (lane == 0) {
+        summed[row] = make_float4(cx, cy, cz, 0.0f);
+        if (fastRow != nullptr && row < fastRowCount) fastRow[row] = makeColor<FAST>(cx, cy, cz);
     }
 }
 
@@ -718,6 +938,7 @@ __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc));
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
                                                             uchar4* __restrict__ fastRow, int fastRowCount)
 {
@@ -765,7 +986,7 @@ __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restr
     // written here instead of by a separate projection launch.  Warp 0 holds (row, channel) at lane 3*row+ch.
     if (fastRow != nullptr && t < 32) {
         const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
-        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor(sum, g, b);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor<FAST>(sum, g, b);
     }
 }
 
@@ -793,10 +1014,11 @@ __device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uns
 }
 __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
 {
-    asm volatile("{\n.reg .pred p;\nCR_MBAR_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CR_MBAR_DONE;\nbra CR_MBAR_WAIT;\nCR_MBAR_DONE:\n}"
+    asm volatile("{\n.reg .pred p;\nCR_MBAR_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CR_MBAR_DONE_%=;\nbra CR_MBAR_WAIT_%=;\nCR_MBAR_DONE_%=:\n}"
                  ::"r"(smemAddr(bar)), "r"(parity) : "memory");
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
                                                       uchar4* __restrict__ fastRow, int fastRowCount)
 {
@@ -847,14 +1069,14 @@ __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ 
     if (summing) reinterpret_cast<float*>(summed + row0 + myRow)[ch] = sum;
     if (fastRow != nullptr) {
         const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
-        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor(sum, g, b);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor<FAST>(sum, g, b);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: vector projections (shaders.cu:375-406) and raw samples (shaders.cu:354-369)
 // ------------------------------------------------------------------------------------------
-__global__ void k_projectVector(int mode, const float4* __restrict__ summed, int N, uchar4* __restrict__ frame, int W, int H)
+__global__ void k_projectVector(int mode, bool fast, const float4* __restrict__ summed, int N, uchar4* __restrict__ frame, int W, int H)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -867,16 +1089,16 @@ __global__ void k_projectVector(int mode, const float4* __restrict__ summed, int
         idx = (uint32_t)(((unsigned long long)(uint32_t)x * (unsigned long long)N) / (unsigned long long)(uint32_t)W);
     }
     const float4 c = __ldg(summed + idx);
-    frame[(size_t)y * W + x] = makeColor(c.x, c.y, c.z);
+    frame[(size_t)y * W + x] = makeColorMode(fast, c.x, c.y, c.z);
 }
 
-__global__ void k_projectRaw(const float* __restrict__ samples, int N, int S, uchar4* __restrict__ frame, int W, int H)
+__global__ void k_projectRaw(bool fast, const float* __restrict__ samples, int N, int S, uchar4* __restrict__ frame, int W, int H)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= W || y >= H || y >= S || x >= N) return;
     const float* p = samples + 3 * ((size_t)x * S + y);             // sample buffer is laid out [o][s]
-    frame[(size_t)y * W + x] = makeColor(p[0], p[1], p[2]);
+    frame[(size_t)y * W + x] = makeColorMode(fast, p[0], p[1], p[2]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -941,7 +1163,7 @@ k_buildProjectionMap(int mode, const float4* __restrict__ omm, int N, uint32_t* 
     if (live) map[p] = closest;
 }
 
-__global__ void k_projectMap(bool ids, const uint32_t* __restrict__ map, const float4* __restrict__ summed,
+__global__ void k_projectMap(bool ids, bool fast, const uint32_t* __restrict__ map, const float4* __restrict__ summed,
                              uchar4* __restrict__ frame, long long nPix)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -952,13 +1174,14 @@ __global__ void k_projectMap(bool ids, const uint32_t* __restrict__ map, const f
                                (unsigned char)((idx >> 8) & 0xff), (unsigned char)(idx & 0xff));
     } else {
         const float4 c = __ldg(summed + idx);
-        frame[p] = makeColor(c.x, c.y, c.z);
+        frame[p] = makeColorMode(fast, c.x, c.y, c.z);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // K4: ordinary cameras (shaders.cu:198-333), tmin 0.01, one primary ray per pixel.
 // ------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(128)
 k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1, float s2, uchar4* __restrict__ frame, int W, int H)
 {
@@ -976,8 +1199,8 @@ k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1,
     } else if (kind == 1) {
         const float ax = dx * (-crm::kPi) + crm::kPi / 2.0f, ay = dy * (crm::kPi / 2.0f) + 0.0f;
         float sax, cax, say, cay;
-        crm::sincos(ax, sax, cax);
-        crm::sincos(ay, say, cay);
+        Fn<FAST>::sincos(ax, sax, cax);
+        Fn<FAST>::sincos(ay, say, cay);
         const V3 od = mk(cax * cay, say, sax * cay);
         ray.d = vnormalize(vadd(vadd(vmuls(X, od.x), vmuls(Y, od.y)), vmuls(Z, od.z)));
         ray.o = vadd(C, vmuls(ray.d, s0));
@@ -987,8 +1210,8 @@ k_camera(const DeviceScene sc, int kind, const DevicePose P, float s0, float s1,
     }
     ray.tmin = 0.01f;
     const Hit h = traceClosest<false>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], 128, nullptr, nullptr);
-    const V3 col = (h.prim >= 0) ? shadeHit(sc, h) : shadeMiss(sc.missShader, ray.d);
-    frame[p] = makeColor(col.x, col.y, col.z);
+    const V3 col = (h.prim >= 0) ? shadeHit<FAST>(sc, h) : shadeMiss<FAST>(sc.missShader, ray.d);
+    frame[p] = makeColor<FAST>(col.x, col.y, col.z);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1057,52 +1280,81 @@ void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t str
     k_prepOmmatidia<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(omm, N, pre);
 }
 
+template <bool FUSED, bool FAST>
+static void launchTraceT(const DeviceScene& sc, const EyeParams& eye, int grid, cudaStream_t stream)
+{
+    if (eye.poses) k_traceCompound<false, true, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    else k_traceCompound<false, false, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+}
+
+template <bool FAST>
+static void launchSumT(const EyeParams& eye, cudaStream_t stream)
+{
+    const long long nf = (long long)eye.N * eye.nFrames;
+    if (eye.fused) {
+        k_sumPartials<FAST><<<(unsigned)((nf * 32 + 127) / 128), 128, 0, stream>>>(eye.partials, (int)nf, eye.S >> 5, eye.summed, eye.fastRow,
+                                                                                  eye.fastRowCount);
+        return;
+    }
+    static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();
+    const unsigned sumGrid = (unsigned)((nf + kSumRows - 1) / kSumRows);
+    if (useTma && eye.S % 4 == 0)
+        k_sumSamplesTma<FAST><<<sumGrid, 32, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+    else
+        k_sumSamples<FAST><<<sumGrid, kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+}
+
+// K1 + K1b.  eye.fused (needs S % 32 == 0 and eye.partials) selects the in-kernel reduction, eye.fast the hardware
+// elementary functions; the per-ray dump exists for the ordered single-frame kernel only.
 void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream)
 {
     const long long total = (long long)eye.N * eye.S;
     if (total <= 0) return;
     const long long need = (total + kTraceThreads - 1) / kTraceThreads;
     const int grid = (int)(need < gridBlocks ? need : gridBlocks);
-    if (eye.dumpHits) k_traceCompound<true, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
-    else if (eye.poses) k_traceCompound<false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
-    else k_traceCompound<false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
-    const long long nf = (long long)eye.N * eye.nFrames;
-    static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();
-    const unsigned sumGrid = (unsigned)((nf + kSumRows - 1) / kSumRows);
-    if (useTma && eye.S % 4 == 0)
-        k_sumSamplesTma<<<sumGrid, 32, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
-    else
-        k_sumSamples<<<sumGrid, kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+    if (eye.dumpHits) {
+        if (eye.fast) k_traceCompound<true, false, false, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+        else k_traceCompound<true, false, false, false><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    } else if (eye.fused) {
+        if (eye.fast) launchTraceT<true, true>(sc, eye, grid, stream);
+        else launchTraceT<true, false>(sc, eye, grid, stream);
+    } else {
+        if (eye.fast) launchTraceT<false, true>(sc, eye, grid, stream);
+        else launchTraceT<false, false>(sc, eye, grid, stream);
+    }
+    if (eye.fast) launchSumT<true>(eye, stream);
+    else launchSumT<false>(eye, stream);
 }
 
-void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, cudaStream_t stream)
+void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, int* lists, cudaStream_t stream)
 {
     const long long total = (long long)eye.N * (eye.poses ? eye.nFrames : 1) * kEntryK;
     if (total <= 0) return;
-    k_buildEntries<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(sc, eye, entries);
+    k_buildEntries<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(sc, eye, entries, lists);
 }
+int candidateListStride() { return kListStride; }
 
 int traceKernelOccupancy()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false, true>, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false, true, false, false>, kTraceThreads, 0);
     return n > 0 ? n : 1;
 }
 
-void launchProjectVector(int mode, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream)
+void launchProjectVector(int mode, bool fast, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream)
 {
     if (W <= 0 || H <= 0) return;
     const int rows = (mode == PROJ_SINGLE_DIM_FAST) ? 1 : H;
     dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows);
-    k_projectVector<<<grid, 128, 0, stream>>>(mode, summed, N, frame, W, H);
+    k_projectVector<<<grid, 128, 0, stream>>>(mode, fast, summed, N, frame, W, H);
 }
 
-void launchProjectRaw(const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream)
+void launchProjectRaw(bool fast, const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream)
 {
     if (W <= 0 || H <= 0) return;
     const int rows = H < S ? H : S;
     dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows);
-    k_projectRaw<<<grid, 128, 0, stream>>>(samples, N, S, frame, W, H);
+    k_projectRaw<<<grid, 128, 0, stream>>>(fast, samples, N, S, frame, W, H);
 }
 
 void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream)
@@ -1112,19 +1364,20 @@ void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map,
     k_buildProjectionMap<<<(unsigned)((nPix + kMapThreads - 1) / kMapThreads), kMapThreads, 0, stream>>>(mode, omm, N, map, W, H);
 }
 
-void launchProjectMap(bool ids, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream)
+void launchProjectMap(bool ids, bool fast, const uint32_t* map, const float4* summed, uchar4* frame, int W, int H, cudaStream_t stream)
 {
     const long long nPix = (long long)W * H;
     if (nPix <= 0) return;
-    k_projectMap<<<(unsigned)((nPix + 255) / 256), 256, 0, stream>>>(ids, map, summed, frame, nPix);
+    k_projectMap<<<(unsigned)((nPix + 255) / 256), 256, 0, stream>>>(ids, fast, map, summed, frame, nPix);
 }
 
-void launchCamera(const DeviceScene& sc, int kind, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame, int W,
+void launchCamera(const DeviceScene& sc, int kind, bool fast, const DevicePose& pose, float s0, float s1, float s2, uchar4* frame, int W,
                   int H, cudaStream_t stream)
 {
     const long long nPix = (long long)W * H;
     if (nPix <= 0) return;
-    k_camera<<<(unsigned)((nPix + 127) / 128), 128, 0, stream>>>(sc, kind, pose, s0, s1, s2, frame, W, H);
+    if (fast) k_camera<true><<<(unsigned)((nPix + 127) / 128), 128, 0, stream>>>(sc, kind, pose, s0, s1, s2, frame, W, H);
+    else k_camera<false><<<(unsigned)((nPix + 127) / 128), 128, 0, stream>>>(sc, kind, pose, s0, s1, s2, frame, W, H);
 }
 
 void launchTraceRays(const DeviceScene& sc, const float* origins, const float* dirs, const float* tmins, int n, int4* hits,

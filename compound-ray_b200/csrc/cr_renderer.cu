@@ -60,6 +60,9 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_ENTRY_FRONTIER")) entryFrontier = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MIN_S")) entryMinSamples = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MIN_RAYS")) entryMinRays = atoll(e);
+    if (const char* e = getenv("CR_REDUCE")) fusedReduce = (std::string(e) == "fused" || std::string(e) == "1");
+    if (const char* e = getenv("CR_FAST_MATH")) fastMath = atoi(e) != 0;
+    if (const char* e = getenv("CR_CANDIDATE_LISTS")) candidateLists = atoi(e);
 }
 Renderer::~Renderer()
 {
@@ -119,8 +122,10 @@ void Renderer::freeCompound(CompoundState& cs)
 {
     dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
-    dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries);
+    dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries); dfree(cs.dPartials); dfree(cs.dLists);
     cs.entryCap = 0;
+    cs.listCap = 0;
+    cs.partialCap = 0;
     cs.batchSampleCap = cs.batchSummedCap = cs.batchPoseCap = 0;
     cs.dumpCap = 0;
     cs.rngN = cs.rngS = 0;
@@ -394,6 +399,7 @@ bool Renderer::entryFrontierActive(const CompoundState& cs, int frames) const
 
 void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
 {
+    cs.listsLast = 0;
     if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1)) return;
     const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(ep.poses ? ep.nFrames : 1);
     if (cs.entryCap < need) {
@@ -401,14 +407,45 @@ void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
         cs.dEntries = dallocT<int4>(need);
         cs.entryCap = need;
     }
-    launchBuildEntries(dscene_, ep, cs.dEntries, stream_);
+    // candidate lists only where K1 can use them: whole warps per ommatidium (S % 32 == 0)
+    const bool wantLists = candidateLists && cs.S % 32 == 0;
+    if (wantLists && cs.listCap < need) {
+        dfree(cs.dLists);
+        cs.dLists = dallocT<int>(need * static_cast<size_t>(candidateListStride()));
+        cs.listCap = need;
+    }
+    launchBuildEntries(dscene_, ep, cs.dEntries, wantLists ? cs.dLists : nullptr, stream_);
     launches_++;
     ep.entries = cs.dEntries;
+    ep.lists = wantLists ? cs.dLists : nullptr;
+    cs.listsLast = wantLists ? need : 0;
+}
+
+// The in-kernel reduction needs whole warps per ommatidium (S % 32 == 0) and is bypassed where somebody reads the
+// per-sample buffer: the raw_ommatidial_samples projection and the per-ray dump.
+bool Renderer::fusedActive(const CompoundState& cs, const HostCamera& cam) const
+{
+    return fusedReduce && cs.S % 32 == 0 && !dumpRays && projectionFromName(cam.projection) != PROJ_RAW_SAMPLES;
+}
+
+void Renderer::ensurePartials(CompoundState& cs, size_t frames)
+{
+    const size_t need = frames * static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S / 32);
+    if (cs.partialCap >= need && cs.dPartials) return;
+    dfree(cs.dPartials);
+    cs.dPartials = dallocT<float4>(need);
+    cs.partialCap = need;
 }
 
 void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow, int fastRowCount)
 {
     EyeParams ep;
+    ep.fast = fastMath;
+    if (fusedActive(cs, cam)) {
+        ensurePartials(cs, 1);
+        ep.fused = true;
+        ep.partials = cs.dPartials;
+    }
     ep.fastRow = fastRow;
     ep.fastRowCount = fastRowCount;
     ep.pre = cs.dPre;
@@ -441,6 +478,11 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
                                    uchar4* fastRow)
 {
     EyeParams ep;
+    ep.fast = fastMath;
+    if (dSamples == nullptr) {             // fused reduction: the caller sized cs.dPartials for nFrames
+        ep.fused = true;
+        ep.partials = cs.dPartials;
+    }
     ep.fastRow = fastRow;
     ep.fastRowCount = fastRow ? cs.N * nFrames : 0;
     ep.pre = cs.dPre;
@@ -463,12 +505,12 @@ void Renderer::project(CompoundState& cs, const HostCamera& cam)
     const int mode = projectionFromName(cam.projection);
     switch (mode) {
         case PROJ_RAW_SAMPLES:
-            launchProjectRaw(cs.dSamples, cs.N, cs.S, dFrame_, W_, H_, stream_);
+            launchProjectRaw(fastMath, cs.dSamples, cs.N, cs.S, dFrame_, W_, H_, stream_);
             launches_++;
             break;
         case PROJ_SINGLE_DIM:
         case PROJ_SINGLE_DIM_FAST:
-            launchProjectVector(mode, cs.dSummed, cs.N, dFrame_, W_, H_, stream_);
+            launchProjectVector(mode, fastMath, cs.dSummed, cs.N, dFrame_, W_, H_, stream_);
             launches_++;
             break;
         case PROJ_UNKNOWN:
@@ -484,7 +526,7 @@ void Renderer::project(CompoundState& cs, const HostCamera& cam)
                 cs.mapMode = mode; cs.mapW = W_; cs.mapH = H_; cs.mapEyeVersion = cs.eyeVersion;
             }
             const bool ids = (mode == PROJ_SPH_ORIENTATIONWISE_IDS || mode == PROJ_SPH_POSITIONWISE_IDS);
-            launchProjectMap(ids, cs.dMap, cs.dSummed, dFrame_, W_, H_, stream_);
+            launchProjectMap(ids, fastMath, cs.dMap, cs.dSummed, dFrame_, W_, H_, stream_);
             launches_++;
             break;
         }
@@ -535,7 +577,7 @@ double Renderer::renderFrame()
         timedTrace = wantTraceEvents_;
         if (!fused) project(cs, cam);
     } else {
-        launchCamera(dscene_, static_cast<int>(cam.kind), toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
+        launchCamera(dscene_, static_cast<int>(cam.kind), fastMath, toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
                      W_, H_, stream_);
         launches_++;
     }
@@ -626,13 +668,17 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
     if (!dOut) { dTmp = dallocT<uchar4>(N * count); dOut = dTmp; }
     // frames per launch: bounded by a sample-buffer budget (12 B per ray per frame)
     const size_t raysPerFrame = N * static_cast<size_t>(cs.S);
+    const bool fused = fusedReduce && cs.S % 32 == 0 && !dumpRays;
     size_t budget = size_t(4) << 30;   // 8 -> 16 -> 32 -> 64 frames per launch: 18.8 -> 19.3 -> 19.6 -> 19.9 Grays/s on the headline workload
     if (const char* env = getenv("CR_BATCH_BYTES")) budget = static_cast<size_t>(atoll(env));
-    size_t F = std::max<size_t>(1, std::min<size_t>(count, budget / std::max<size_t>(1, raysPerFrame * 12)));
+    // bytes per ray and frame held between K1 and K1b: 12 (ordered: one float3 per sample) or 0.5 (fused: one float4 per warp)
+    size_t F = std::max<size_t>(1, std::min<size_t>(count, fused ? size_t(256) : budget / std::max<size_t>(1, raysPerFrame * 12)));
     if (const char* env = getenv("CR_BATCH_FRAMES")) F = std::max<size_t>(1, std::min<size_t>(count, static_cast<size_t>(atoll(env))));
     if (dumpRays) F = 1;
     lastBatchFrames_ = static_cast<int>(F);
-    if (cs.batchSampleCap < F * raysPerFrame * 3) {
+    if (fused) {
+        ensurePartials(cs, F);
+    } else if (cs.batchSampleCap < F * raysPerFrame * 3) {
         dfree(cs.dBatchSamples);
         cs.dBatchSamples = dallocT<float>(F * raysPerFrame * 3);
         cs.batchSampleCap = F * raysPerFrame * 3;
@@ -643,10 +689,15 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
         cs.batchSummedCap = F * N;
     }
-    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.entryCap < F * N) {   // keep the allocation out of the timed region
+    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.entryCap < F * N) {   // keep the allocations out of the timed region
         dfree(cs.dEntries);
         cs.dEntries = dallocT<int4>(F * N);
         cs.entryCap = F * N;
+    }
+    if (entryFrontierActive(cs, static_cast<int>(F)) && candidateLists && cs.S % 32 == 0 && cs.listCap < F * N) {
+        dfree(cs.dLists);
+        cs.dLists = dallocT<int>(F * N * static_cast<size_t>(candidateListStride()));
+        cs.listCap = F * N;
     }
     if (cs.batchPoseCap < count) {
         dfree(cs.dBatchPoses);
@@ -673,7 +724,7 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
             pose.pos = {q[0], q[1], q[2]}; pose.ax = {q[3], q[4], q[5]}; pose.ay = {q[6], q[7], q[8]}; pose.az = {q[9], q[10], q[11]};
             launchCompound(cs, cam, pose, dOut + p0 * N, cs.N);
         } else {
-            launchCompoundBatch(cs, cs.dBatchPoses + p0, static_cast<int>(Fc), cs.dBatchSamples, cs.dBatchSummed, dOut + p0 * N);
+            launchCompoundBatch(cs, cs.dBatchPoses + p0, static_cast<int>(Fc), fused ? nullptr : cs.dBatchSamples, cs.dBatchSummed, dOut + p0 * N);
         }
     }
     CR_CUDA(cudaEventRecord(evB_, stream_));
@@ -721,6 +772,16 @@ size_t Renderer::debugCopyLastRays(float* origins, float* dirs, int32_t* hits4)
     CR_CUDA(cudaMemcpy(origins, cs.dDumpO, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     CR_CUDA(cudaMemcpy(dirs, cs.dDumpD, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     CR_CUDA(cudaMemcpy(hits4, cs.dDumpH, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+size_t Renderer::debugCopyCandidateLists(int32_t* out, size_t records)
+{
+    if (!compoundActive()) return 0;
+    CompoundState& cs = compoundState(current_);
+    const size_t n = std::min(records, cs.listsLast);
+    if (!cs.dLists || n == 0) return 0;
+    CR_CUDA(cudaMemcpy(out, cs.dLists, sizeof(int) * n * static_cast<size_t>(candidateListStride()), cudaMemcpyDeviceToHost));
     return n;
 }
 

@@ -38,6 +38,9 @@ struct CompoundState {                 // device side of one CompoundEye camera
     float* dBatchSamples = nullptr; float4* dBatchSummed = nullptr; DevicePose* dBatchPoses = nullptr;
     size_t batchSampleCap = 0, batchSummedCap = 0, batchPoseCap = 0;
     int4* dEntries = nullptr; size_t entryCap = 0;   // entry frontier [frames][N] (k_buildEntries)
+    int* dLists = nullptr; size_t listCap = 0;       // candidate lists [frames][N][16] (k_buildEntries stage 2)
+    size_t listsLast = 0;                            // records written by the last launch (0: lists not built)
+    float4* dPartials = nullptr; size_t partialCap = 0;   // fused reduction: [frames][N][S/32] warp partials
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; int2* dDumpC = nullptr; size_t dumpCap = 0;
 };
@@ -73,6 +76,11 @@ public:
     int entryFrontier = 1;             // 0: every sample ray starts at the BVH root (A/B switch, crDebugSetEntryFrontier)
     int entryMinSamples = 8;           // below this S (or this many rays per launch) the frontier pass --
     long long entryMinRays = 3ll << 18; // a chain of ~20 dependent node fetches, ~25 us -- costs more than it saves
+    // Render modes (crSetRenderMode; environment CR_REDUCE=fused / CR_FAST_MATH=1 preset them for unmodified scripts).
+    // Default: ordered sum + cr_math.h = every output bit equal to the CPU checker.
+    bool fusedReduce = false;          // K1 sums 32 samples per warp in-kernel (fixed order, RGB equal to rounding) -- no sample buffer
+    bool fastMath = false;             // hardware sin/cos/log/pow, as the reference's --use_fast_math build
+    int candidateLists = 1;            // 0: no per-ommatidium candidate lists (A/B switch, crDebugSetCandidateLists): per-lane walk only
     int width() const { return W_; }
     int height() const { return H_; }
 
@@ -92,6 +100,7 @@ public:
     int debugNodeCount() const { return bvh_.nNodes; }
     void debugCopyRngStates(uint32_t* out8);                      // [N*S][8] in reference stream-id order
     size_t debugCopyLastRayCounts(int32_t* counts2);
+    size_t debugCopyCandidateLists(int32_t* out, size_t records);   // 16 ints per (frame, ommatidium) of the last launch
     size_t debugCopyLastRays(float* origins, float* dirs, int32_t* hits4);
     void debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8);
     void debugCopyProjectionMap(uint32_t* out);
@@ -107,6 +116,8 @@ private:
     void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow = nullptr, int fastRowCount = 0);
     void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
                              uchar4* fastRow = nullptr);
+    bool fusedActive(const CompoundState& cs, const HostCamera& cam) const;
+    void ensurePartials(CompoundState& cs, size_t frames);
     bool entryFrontierActive(const CompoundState& cs, int frames) const;   // frames = poses covered by the launch
     void buildEntries(CompoundState& cs, EyeParams& ep);
     void project(CompoundState& cs, const HostCamera& cam);

@@ -107,6 +107,12 @@ def configureFunctions(eyeRenderer):
     r.crRenderPoseBatch.restype = C.c_double
     r.crSetFirstFrame.argtypes = [C.c_uint64]
     r.crSetOmmatidialShard.argtypes = [C.c_uint64, C.c_uint64]
+    r.crSetRenderMode.argtypes = [C.c_int, C.c_int]
+    r.crGetRenderMode.restype = C.c_int
+    r.crDebugSetCandidateLists.argtypes = [C.c_int]
+    r.crDebugCopyCandidateLists.argtypes = [vp, C.c_size_t]
+    r.crDebugCopyCandidateLists.restype = C.c_size_t
+    r.crGetLastBatchFrames.restype = C.c_int
     r.crGetLastTraceMs.restype = C.c_double
     r.crGetLaunchCount.restype = C.c_ulonglong
     r.crGetBvhBuildMs.restype = C.c_double
@@ -242,6 +248,12 @@ def getOmmatidialData(eyeRenderer):
     out = np.zeros((n, 3), dtype=np.float32)
     eyeRenderer.crGetOmmatidialData(out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def setRenderMode(eyeRenderer, fused=None, fast_math=None):
+    """Addition: crSetRenderMode.  fused=True: in-kernel reduction (fixed order, RGB equal to fp32 rounding);
+    fast_math=True: hardware sin/cos/log/pow as in the reference's --use_fast_math build.  None keeps a switch."""
+    eyeRenderer.crSetRenderMode(-1 if fused is None else int(bool(fused)), -1 if fast_math is None else int(bool(fast_math)))
 
 
 def make_poses(positions, x=(1, 0, 0), y=(0, 1, 0), z=(0, 0, 1)):

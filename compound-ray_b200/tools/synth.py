@@ -152,3 +152,145 @@ def write_terrain_gltf(path, triangles=1_000_000, extent=1000.0, amplitude=15.0,
     with open(os.path.join(os.path.dirname(path), bin_name), "wb") as f:
         f.write(bytes(blob))
     return {"triangles": int(len(idx)), "vertices": int(len(pos)), "camera_position": [0.0, cam_y, 0.0]}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 3: the "ofstad arena" of data/tools/minimumSampleRateFinder.py.  The reference's own
+# data/ofstad-arena/ofstad-arena.gltf and ofstad_patterning.jpg are not in the checkout; SURVEY 8(d)3 fixes the
+# stand-in: an open cylinder of radius 12.5 and height 9.19 (the bounds the script samples inside,
+# minimum-samples-calculation/readme.txt:15), 256 segments x 64 rings = 32 768 triangles, a 1024^2 black/white
+# rectangle pattern on its inside -- written as a JPEG so that the product's own decoder is on the path --, a floor
+# disc, default background, a compound camera and a panoramic camera at the centre.
+# ------------------------------------------------------------------------------------------------
+ARENA_RADIUS = 12.5
+ARENA_HEIGHT = 9.19
+
+
+def arena_pattern(size=1024, seed=3):
+    """uint8[size][size][3]: white wall with black rectangles of assorted widths/heights (a stand-in for the bars,
+    boxes and gratings of the Ofstad et al. arena)."""
+    rng = np.random.default_rng(seed)
+    img = np.full((size, size, 3), 255, np.uint8)
+    for k in range(48):
+        w = int(rng.integers(size // 64, size // 6))
+        h = int(rng.integers(size // 32, size // 2))
+        x = int(rng.integers(0, size - w))
+        y = int(rng.integers(0, size - h))
+        img[y:y + h, x:x + w] = 0 if k % 5 else 96
+    # one grating sector: 16 vertical bars
+    gx0 = size // 8
+    for b in range(16):
+        if b % 2 == 0:
+            img[size // 2:size // 2 + size // 4, gx0 + b * (size // 64):gx0 + (b + 1) * (size // 64)] = 0
+    return img
+
+
+def write_arena_gltf(path, segments=256, rings=64, radius=ARENA_RADIUS, height=ARENA_HEIGHT, eye_file="eye.eye",
+                     projection="single_dimension_fast", camera_height=None, texture="jpeg", jpeg_quality=92):
+    """Writes <path> (.gltf) + <path>.bin + the pattern image next to it.  Returns dict(triangles, ...).
+    texture = "jpeg" | "png" (needs PIL to write the image) | "none" (white wall, base colour only)."""
+    th = np.arange(segments + 1, dtype=np.float64) / segments * 2.0 * math.pi
+    ys = np.arange(rings + 1, dtype=np.float64) / rings * height
+    T, Y = np.meshgrid(th, ys, indexing="xy")                        # [rings+1][segments+1]
+    wall = np.stack([radius * np.cos(T), Y, radius * np.sin(T)], axis=-1).reshape(-1, 3).astype(np.float32)
+    wall_uv = np.stack([T / (2.0 * math.pi), 1.0 - Y / height], axis=-1).reshape(-1, 2).astype(np.float32)
+    n1 = segments + 1
+    ii, jj = np.meshgrid(np.arange(segments), np.arange(rings), indexing="xy")
+    v00 = (jj * n1 + ii).reshape(-1).astype(np.uint32)
+    v10, v01, v11 = v00 + 1, v00 + n1, v00 + n1 + 1
+    wall_idx = np.stack([np.stack([v00, v10, v11], 1), np.stack([v00, v11, v01], 1)], axis=1).reshape(-1, 3).astype(np.uint32)
+    # floor disc: fan of `segments` triangles, plain grey material (the base-colour path of the shader)
+    floor = np.concatenate([np.zeros((1, 3)), np.stack([radius * np.cos(th[:-1]), np.zeros(segments), radius * np.sin(th[:-1])], 1)]).astype(np.float32)
+    k = np.arange(segments, dtype=np.uint32)
+    floor_idx = np.stack([np.zeros(segments, np.uint32), 1 + k, 1 + (k + 1) % segments], axis=1).astype(np.uint32)
+
+    blob = bytearray()
+    views = []
+
+    def add(arr, target=None):
+        while len(blob) % 4:
+            blob.append(0)
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": arr.nbytes})
+        if target:
+            views[-1]["target"] = target
+        blob.extend(arr.tobytes())
+        return len(views) - 1
+
+    v_wp, v_wuv, v_wi = add(wall, 34962), add(wall_uv, 34962), add(wall_idx.reshape(-1), 34963)
+    v_fp, v_fi = add(floor, 34962), add(floor_idx.reshape(-1), 34963)
+    bin_name = os.path.basename(path) + ".bin"
+    base = os.path.dirname(path)
+    cam_y = float(height * 0.25 if camera_height is None else camera_height)
+    rot_up = [0.7071067690849304, 0, 0, 0.7071067690849304]
+    rot_dn = [-0.7071067690849304, 0, 0, 0.7071067690849304]
+    wall_prim = {"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}
+    materials = [{"name": "wall", "pbrMetallicRoughness": {"baseColorFactor": [1.0, 1.0, 1.0, 1.0]}},
+                 {"name": "floor", "pbrMetallicRoughness": {"baseColorFactor": [0.35, 0.35, 0.35, 1.0]}}]
+    gltf = {
+        "asset": {"version": "2.0", "generator": "compound-ray_b200 tools/synth.py"},
+        "scene": 0,
+        "scenes": [{"name": "Scene", "nodes": [0, 1, 3, 5]}],               # no background-shader extra: default_background
+        "nodes": [
+            {"mesh": 0, "name": "ArenaWall"},
+            {"mesh": 1, "name": "ArenaFloor"},
+            {"camera": 0, "name": "compound-cam_Orientation", "rotation": rot_dn},
+            {"children": [2], "name": "compound-cam", "rotation": rot_up, "translation": [0.0, cam_y, 0.0]},
+            {"camera": 1, "name": "pano-cam_Orientation", "rotation": rot_dn},
+            {"children": [4], "name": "pano-cam", "rotation": rot_up, "translation": [0.0, cam_y, 0.0]},
+        ],
+        "cameras": [
+            {"name": "compound-cam", "type": "perspective", "perspective": {"yfov": 0.4, "znear": 0.1, "zfar": 1000},
+             "extras": {"compound-eye": "true", "compound-projection": projection, "compound-structure": eye_file}},
+            {"name": "pano-cam", "type": "perspective", "perspective": {"yfov": 0.4, "znear": 0.1, "zfar": 1000},
+             "extras": {"panoramic": "true"}},
+        ],
+        "meshes": [{"name": "ArenaWall", "primitives": [wall_prim]},
+                   {"name": "ArenaFloor", "primitives": [{"attributes": {"POSITION": 3}, "indices": 4, "material": 1}]}],
+        "materials": materials,
+        "accessors": [
+            {"bufferView": v_wp, "componentType": 5126, "count": int(len(wall)), "type": "VEC3",
+             "min": [float(v) for v in wall.min(axis=0)], "max": [float(v) for v in wall.max(axis=0)]},
+            {"bufferView": v_wuv, "componentType": 5126, "count": int(len(wall_uv)), "type": "VEC2"},
+            {"bufferView": v_wi, "componentType": 5125, "count": int(wall_idx.size), "type": "SCALAR"},
+            {"bufferView": v_fp, "componentType": 5126, "count": int(len(floor)), "type": "VEC3",
+             "min": [float(v) for v in floor.min(axis=0)], "max": [float(v) for v in floor.max(axis=0)]},
+            {"bufferView": v_fi, "componentType": 5125, "count": int(floor_idx.size), "type": "SCALAR"},
+        ],
+        "bufferViews": views,
+        "buffers": [{"byteLength": len(blob), "uri": bin_name}],
+    }
+    image_name = None
+    if texture in ("jpeg", "png"):
+        from PIL import Image
+        image_name = os.path.basename(path) + (".pattern.jpg" if texture == "jpeg" else ".pattern.png")
+        im = Image.fromarray(arena_pattern())
+        if texture == "jpeg":
+            im.save(os.path.join(base, image_name), format="JPEG", quality=jpeg_quality, subsampling=2)
+        else:
+            im.save(os.path.join(base, image_name), format="PNG")
+        gltf["images"] = [{"uri": image_name}]
+        gltf["samplers"] = [{"magFilter": 9729, "minFilter": 9987, "wrapS": 10497, "wrapT": 10497}]
+        gltf["textures"] = [{"source": 0, "sampler": 0}]
+        materials[0]["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+    with open(path, "w") as f:
+        json.dump(gltf, f)
+    with open(os.path.join(base, bin_name), "wb") as f:
+        f.write(bytes(blob))
+    return {"triangles": int(len(wall_idx) + len(floor_idx)), "wall_triangles": int(len(wall_idx)), "vertices": int(len(wall) + len(floor)),
+            "camera_position": [0.0, cam_y, 0.0], "image": image_name}
+
+
+def ico_eye():
+    """float32[12][8]: the icosahedral 12-ommatidia eye of eyeRendererHelperFunctions.getIcoOmmatidia (:171-194): vertices
+    of an icosahedron, 1 steradian each (acceptance = 2*acos(1 - 1/(2*pi)))."""
+    lat = math.atan(0.5)
+    pts = [[0.0, 1.0, 0.0]]
+    for ring, sign in ((0.0, 1.0), (0.2 * math.pi, -1.0)):
+        for i in range(5):
+            a = 0.4 * math.pi * i + ring
+            pts.append([math.cos(a) * math.cos(lat), sign * math.sin(lat), math.sin(a) * math.cos(lat)])
+    pts.append([0.0, -1.0, 0.0])
+    omm = np.zeros((12, 8), np.float32)
+    omm[:, 3:6] = np.asarray(pts, np.float32)
+    omm[:, 6] = math.acos(-(1 / (2 * math.pi) - 1)) * 2
+    return omm

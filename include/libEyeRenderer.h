@@ -109,6 +109,22 @@ void crSetFirstFrame(uint64_t frame);
  * use the global indices (id = globalCount*s + firstIndex + o, shaders.cu:680-685), so the gathered per-ommatidium
  * results equal the unsharded frame bit for bit.  globalCount = 0 switches back.  Forces a stream initialisation. */
 void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex);
+/* Render modes of the compound path; a negative argument leaves that switch as it is.  Both default to 0 (also preset by
+ * the environment variables CR_REDUCE=fused and CR_FAST_MATH=1, for scripts that cannot call this).
+ *   fusedReduction 0: every sample's colour/S is stored and summed in sample order -- the reference's sequential fp32
+ *                     sum (shaders.cu:341-347, :730); every output bit equals the CPU checker.
+ *                  1: the trace kernel sums the 32 samples of a warp with a shuffle butterfly and a second, tiny kernel
+ *                     adds the S/32 partial sums in a fixed order (needs S % 32 == 0, else the ordered path runs).  Rays,
+ *                     hits and per-sample colours are unchanged; the float RGB per ommatidium agrees with mode 0 to
+ *                     fp32 rounding of a different addition order (~1e-7 relative; 8-bit frames differ in < 1e-4 of
+ *                     the bytes, by one step).  No per-sample buffer: 12 B/ray of HBM traffic become 0.5 B/ray.
+ *   fastMath       0: sin/cos/log/pow/asin/atan2 are the specified binary32 algorithms of csrc/cr_math.h.
+ *                  1: the hardware approximations (__sincosf, __logf, __powf) the reference itself runs -- its device
+ *                     code is built with --use_fast_math (CMakeLists.txt:142).  Rays differ in the last bits; the mode
+ *                     is held to max |dRGB| <= 1/255, mean <= 1e-4 against the checker, not to bit-exactness.
+ * crGetRenderMode returns fusedReduction | fastMath << 1. */
+void crSetRenderMode(int fusedReduction, int fastMath);
+int crGetRenderMode(void);
 /* CUDA-event time of the last compound trace launch(es), milliseconds (crRenderPoseBatch: always; renderFrame: from the
  * first call of this function on -- until then the host-side frame time is returned, so that untimed loops pay no events). */
 double crGetLastTraceMs(void);
@@ -146,6 +162,15 @@ void crDebugSetRayDump(bool on);
 /* A/B switch of the per-ommatidium entry frontier (default: on for S >= 8 and N*S >= 786432 rays per frame);
  * negative thresholds keep the current value. */
 void crDebugSetEntryFrontier(int on, int minSamples, long long minRaysPerFrame);
+/* A/B switch of the per-ommatidium candidate lists (default on; they need the entry frontier and S % 32 == 0): the
+ * frontier pass also flattens what an ommatidium's sample cone can reach into a list of <= 15 pre-leaf BVH nodes, which
+ * the 32 samples a warp holds of that ommatidium test in lockstep instead of walking the tree per lane.  The closest
+ * hit is the same either way. */
+void crDebugSetCandidateLists(int on);
+/* The candidate lists of the last trace launch: 16 ints per (frame, ommatidium) -- [0] = element count (-1: none, the
+ * frontier is walked per lane; 0: the cone reaches no leaf), [1..] = node << 2 | reachable-leaf mask.  Returns the
+ * number of records copied (<= records; 0 when the launch built none). */
+size_t crDebugCopyCandidateLists(int32_t* out, size_t records);
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* stream-id order N*s+o */
 size_t crDebugCopyLastRayCounts(int32_t* counts2); /* (BVH nodes fetched, triangles tested) per dumped ray, same order */
 void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */

@@ -60,15 +60,33 @@ def build(force=False):
     return _LIB_PATH
 
 
+def build_native(out_dir):
+    """The SAME source compiled for the machine this runs on (`gcc -O3 -march=native`, still without contraction or
+    fast-math, so the bits do not change): the CPU-baseline timing build of bench.py.  It is compiled where
+    it is timed -- never shipped -- because -march=native code built on one host may not run on another.  Returns the
+    path, or None when there is no compiler."""
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libcr_oracle_native.so")
+    cmd = ["gcc", "-O3", "-march=native", "-std=c11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+           "-fvisibility=hidden", "-shared", "-o", out, os.path.join(_HERE, "cr_oracle.c"), "-lm"]
+    try:
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+    return out
+
+
 _lib = None
 
 
 def lib():
+    """The checker library.  CR_ORACLE_SO (set by bench.py's CPU-baseline subprocess) selects another build of it."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        path = os.environ.get("CR_ORACLE_SO") or _LIB_PATH
+        if path == _LIB_PATH and not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(path)
         vp, i64, f32 = C.c_void_p, C.c_int64, C.c_float
         L.cro_xorwow_init.argtypes = [C.POINTER(XwState), C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]
         L.cro_xorwow_skipahead.argtypes = [C.POINTER(XwState), C.c_ulonglong]
@@ -245,6 +263,32 @@ def projection_map(omm, mode, W, H):
     out = np.empty((H, W), dtype=np.uint32)
     lib().cro_projection_map(_p(omm), len(omm), PROJECTIONS[mode], W, H, _p(out))
     return out
+
+
+def fused_sum(compound, N, S):
+    """Per-ommatidium RGB in the FIXED addition order of the product's fused reduction (crSetRenderMode(1, .);
+    k_traceCompound<FUSED> + k_sumPartials in csrc/cr_kernels.cu), restated on the checker's per-sample colours
+    (`compound`: [S*N][3] in stream-id order N*s+o, already divided by S, shaders.cu:730):
+      1. samples 32b .. 32b+31 of an ommatidium are combined by a butterfly -- level d in (16, 8, 4, 2, 1) adds
+         element i and element i+d of the surviving 2d elements;
+      2. "lane" l adds the block sums l, l+32, l+64, ... in ascending order, starting from 0;
+      3. the same butterfly combines the 32 lanes.
+    The reference's own order is the plain sequential sum (shaders.cu:341-347) -- cro_accumulate; the two differ by
+    fp32 rounding only."""
+    assert S % 32 == 0
+    c = np.ascontiguousarray(compound, dtype=np.float32).reshape(S, N, 3).transpose(1, 0, 2).reshape(N, S // 32, 32, 3)
+
+    def butterfly(a):                                   # [..., 32, 3] -> [..., 3]
+        for d in (16, 8, 4, 2, 1):
+            a = a[..., :d, :] + a[..., d:2 * d, :]
+        return a[..., 0, :]
+
+    blocks = butterfly(c)                               # [N][S/32][3]
+    lanes = np.zeros((N, 32, 3), dtype=np.float32)
+    for k in range(0, S // 32, 32):
+        part = blocks[:, k:k + 32]
+        lanes[:, :part.shape[1]] = lanes[:, :part.shape[1]] + part
+    return butterfly(lanes).astype(np.float32)
 
 
 class CompoundEyeOracle:
