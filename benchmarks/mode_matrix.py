@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--samples", type=int, default=1024)
     ap.add_argument("--triangles", type=int, default=1_000_000)
     ap.add_argument("--ommatidia", type=int, default=10_000)
-    ap.add_argument("--lists", default="0,1")
+    ap.add_argument("--lists", default="0,1", help="crDebugSetCandidateLists values: 0 never, 1 batches only (default), 2 always")
     ap.add_argument("--e2e-frames", type=int, default=20)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
@@ -45,7 +45,7 @@ def main():
     rows = []
     ref_rows = None
     # candidate-list statistics of one frame
-    lib.crDebugSetCandidateLists(1)
+    lib.crDebugSetCandidateLists(2)
     lib.setCurrentEyeSamplesPerOmmatidium(S)
     lib.renderFrame()
     rec = np.zeros((N, 16), np.int32)

@@ -29,6 +29,10 @@ def main():
     ap.add_argument("--poses", type=int, default=512)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--native", action="store_true", help="the library's own NCCL data plane (crRenderPoseBatchSharded, csrc/cr_comm.cpp): "
+                    "every rank passes all poses; the C++ host shards, positions the streams and gathers")
+    ap.add_argument("--id-file", default=None, help="--native without torch.distributed: file that carries the NCCL unique id")
+    ap.add_argument("--mode", default="ordered", choices=["ordered", "fused", "fused_fast"])
     args = ap.parse_args()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -38,13 +42,15 @@ def main():
     import speed_test
     from tools import synth
     data = speed_test.fixtures()
-    if world > 1:
+    use_torch = world > 1 and not (args.native and args.id_file)
+    if use_torch:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = er.load_library(device=local)
     lib.setVerbosity(False)
+    lib.crSetRenderMode({"ordered": 0, "fused": 1, "fused_fast": 1}[args.mode], 1 if args.mode == "fused_fast" else 0)
     lib.loadGlTFscene(os.path.join(data, "sim-environment", "env_2.gltf").encode())
     lib.gotoCameraByName(b"compound-cam")
     base = np.array([[*o.position, *o.direction, o.acceptanceAngle, o.focalpointOffset] for o in
@@ -59,11 +65,24 @@ def main():
     lib.crDebugCopyCameraPose(pose.ctypes.data)
     pos = np.random.default_rng(0).uniform(-25, 25, (P, 3)).astype(np.float32)
     lo, hi = sharding.pose_block(rank, world, P)
-    poses = er.make_poses(pos[lo:hi], x=pose[3:6], y=pose[6:9], z=pose[9:12])
+    all_poses = er.make_poses(pos, x=pose[3:6], y=pose[6:9], z=pose[9:12])
+    poses = all_poses[lo:hi]
     lib.crSetFirstFrame(lo)
     er.renderPoseBatch(lib, poses[:min(8, len(poses))])                      # warm-up (then rewind the streams)
     lib.crSetFirstFrame(lo)
-    if args.chunk > 0:
+    if args.native:
+        sharding.init_library_comm(lib, rank, world, dist if use_torch else None, args.id_file)
+        sharding.render_pose_batch_sharded(lib, all_poses[:min(8 * world, P)], chunk=args.chunk)      # warm-up incl. the collective
+        t0 = time.perf_counter()
+        rows, _ = sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk)     # all P rows on every rank, host side
+        dt = time.perf_counter() - t0
+        if use_torch:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        checksum = int(rows.astype(np.int64).sum())
+        lib.crCommDestroy()
+    elif args.chunk > 0:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -108,10 +127,11 @@ def main():
         checksum = int(rows.astype(np.int64).sum())
     if rank == 0:
         out = {"benchmark": "pose batch (BASELINE config 5)", "n_gpus": world, "poses": P, "ommatidia": N, "samples": S,
-               "chunk": args.chunk, "seconds": dt, "poses_per_sec": P / dt, "rays_per_sec": P * N * S / dt, "ommatidia_frames_per_sec": P * N / dt,
+               "chunk": args.chunk, "mode": args.mode,
+               "data_plane": "library (crRenderPoseBatchSharded: ncclBroadcast groups per chunk, C++)" if args.native else "torch.distributed", "seconds": dt, "poses_per_sec": P / dt, "rays_per_sec": P * N * S / dt, "ommatidia_frames_per_sec": P * N / dt,
                "checksum": checksum, "timing": "host wall clock incl. pose upload, render, allgather / D2H; max over ranks"}
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
-    if world > 1:
+    if use_torch:
         dist.destroy_process_group()
 
 

@@ -210,6 +210,48 @@ void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex)
     renderer().setOmmatidialShard(globalCount, firstIndex);
     CR_GUARD_END()
 }
+int crCommGetUniqueId(void* out128)
+{
+    CR_GUARD_BEGIN
+    renderer().commUniqueId(out128);
+    return 0;
+    CR_GUARD_END(-1)
+}
+int crCommInit(const void* id128, int nRanks, int rank)
+{
+    CR_GUARD_BEGIN
+    renderer().commInit(id128, nRanks, rank);
+    return 0;
+    CR_GUARD_END(-1)
+}
+void crCommDestroy(void)
+{
+    CR_GUARD_BEGIN
+    renderer().commDestroy();
+    CR_GUARD_END()
+}
+int crCommRank(void) { return renderer().commRank(); }
+int crCommSize(void) { return renderer().commSize(); }
+int crCommNcclVersion(void)
+{
+    CR_GUARD_BEGIN
+    return renderer().commNcclVersion();
+    CR_GUARD_END(0)
+}
+int crAllGatherRows(const void* sendDevice, void* recvDevice, size_t bytesPerRank)
+{
+    CR_GUARD_BEGIN
+    renderer().allGatherRows(sendDevice, recvDevice, bytesPerRank);
+    return 0;
+    CR_GUARD_END(-1)
+}
+double crRenderPoseBatchSharded(const float* poses, size_t count, unsigned char* outHost, void* outDevice, size_t chunkPoses,
+                                uint64_t firstFrame)
+{
+    CR_GUARD_BEGIN
+    return renderer().renderPoseBatchSharded(poses, count, outHost, outDevice, chunkPoses, firstFrame);
+    CR_GUARD_END(-1.0)
+}
 void crSetRenderMode(int fusedReduction, int fastMath)
 {
     if (fusedReduction >= 0) renderer().fusedReduce = fusedReduction != 0;

@@ -334,7 +334,9 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
 
 // Traversal stack: the first kSmemStack levels live in shared memory laid out [level][thread]
 // (bank = thread, conflict-free, 32-bit addressing); deeper levels spill to a per-thread local
-// array (L1-cached).  An LBVH over 63-bit codes plus index tie-breaks is at most 63+28 levels deep.
+// array (L1-cached).  An LBVH over 63-bit codes plus index tie-breaks is at most 63+28 levels deep, and a
+// depth-first walk that pushes one sibling per level never holds more entries than that (+3 frontier entries):
+// kSmemStack + kLocalStack = 96 covers it, so push() needs no bound check.
 #ifndef CR_TRACE_MIN_BLOCKS
 #define CR_TRACE_MIN_BLOCKS 8
 #endif
@@ -343,7 +345,7 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
 #endif                     // with the entry frontier the stack stays shallow, and 5 KB/CTA leaves the SM a 192 KB L1
 
 constexpr int kSmemStack = CR_SMEM_STACK;
-constexpr int kLocalStack = 64;
+constexpr int kLocalStack = 96 - CR_SMEM_STACK;   // shared + local levels >= 96 > the deepest possible LBVH (63 + 28 levels) + 3 entries
 constexpr int kSentinel = (int)0x80000000;
 
 struct Stack {
@@ -726,31 +728,35 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
         }
         L = Nw;
     }
-    if (!live || lane != 0) return;
-    // near to far along the axis (kEntryK = 4: fixed compare-exchange network, empty slots last)
+    // near to far along the axis (kEntryK = 4: fixed compare-exchange network, empty slots last); every lane of the
+    // group holds the same list and sorts it the same way
 #pragma unroll
     for (int k = 0; k < kEntryK; k++) if (k >= L.n) L.key[k] = 3.0e38f;
     auto cswap = [&](int x, int y) {
         if (L.key[x] > L.key[y]) { const float tk = L.key[x]; L.key[x] = L.key[y]; L.key[y] = tk; const int tr = L.ref[x]; L.ref[x] = L.ref[y]; L.ref[y] = tr; }
     };
     cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
-    entries[idx] = make_int4(L.ref[0], L.ref[1], L.ref[2], L.ref[3]);
-    if (lists == nullptr) return;
+    if (live && lane == 0) entries[idx] = make_int4(L.ref[0], L.ref[1], L.ref[2], L.ref[3]);
+    if (lists == nullptr) return;                                  // (uniform)
 
-    // Stage 2: candidate list.  Depth-first from the frontier with the same cone test, flattening what the cone can
-    // reach into "pre-leaf" elements (node << 2 | mask of its children that are reachable LEAVES); reachable internal
-    // children are descended into, nearer child first, so the list runs roughly near to far.  The walk gives up --
-    // header kListFallback, K1 then walks the frontier per lane -- as soon as the cone turns out to reach more than
-    // kListMax elements, after kListVisits nodes, or when the frontier itself was a fallback (ok == false).
-    // Header 0 = the cone reaches no leaf at all (sky): K1 skips traversal.
-    int* out = lists + (size_t)idx * kListStride;
-    constexpr int kListVisits = 48, kListStack = 16;
+    // Stage 2: candidate list.  Lane j walks the subtree of entry j depth-first with the same cone test, flattening
+    // what the cone can reach into "pre-leaf" elements (node << 2 | mask of its children that are reachable LEAVES);
+    // reachable internal children are descended into, nearer child first, so the list runs roughly near to far.  The
+    // four partial lists are concatenated in entry order.  The walk gives up -- header kListFallback, K1 then walks the
+    // frontier per lane -- as soon as the cone turns out to reach more than kListMax elements, after kListVisits nodes
+    // in one subtree, or when the frontier itself was a fallback (ok == false).  Header 0 = the cone reaches no leaf at
+    // all (sky): K1 skips traversal.
+    constexpr int kListVisits = 28, kListStack = 16;
     int stack[kListStack];
+    int el[kListMax];
     int sp = 0, n = 0, visits = 0;
     bool good = ok;
+    {
+        int myRef = kSentinel;
 #pragma unroll
-    for (int k = kEntryK - 1; k >= 0; k--)
-        if (k < L.n) stack[sp++] = L.ref[k];                      // nearest entry on top
+        for (int k = 0; k < kEntryK; k++) if (k == lane && k < L.n) myRef = L.ref[k];
+        if (myRef != kSentinel && good) stack[sp++] = myRef;
+    }
     while (sp > 0 && good) {
         const int node = stack[--sp];
         if (++visits > kListVisits) { good = false; break; }
@@ -763,8 +769,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
         const int mask = ((h0 && r0 < 0) ? 1 : 0) | ((h1 && r1 < 0) ? 2 : 0);
         if (mask) {
             if (n == kListMax) { good = false; break; }
-            out[1 + n] = (node << 2) | mask;
-            n++;
+            el[n++] = (node << 2) | mask;
         }
         const bool d0 = h0 && r0 >= 0, d1 = h1 && r1 >= 0;
         if (d0 && d1) {
@@ -779,7 +784,23 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
             stack[sp++] = d0 ? r0 : r1;
         }
     }
-    out[0] = good ? n : kListFallback;
+    // concatenate: offsets = exclusive prefix of the group's counts; any failure or overflow voids the whole list
+    int before = 0, total = 0;
+    bool allGood = true;
+#pragma unroll
+    for (int j = 0; j < kEntryK; j++) {
+        const int cj = __shfl_sync(0xffffffffu, n, j, kEntryK);
+        const int gj = __shfl_sync(0xffffffffu, good ? 1 : 0, j, kEntryK);
+        if (j < lane) before += cj;
+        total += cj;
+        allGood = allGood && gj != 0;
+    }
+    allGood = allGood && total <= kListMax;
+    if (!live) return;
+    int* out = lists + (size_t)idx * kListStride;
+    if (allGood)
+        for (int i = 0; i < n; i++) out[1 + before + i] = el[i];
+    if (lane == 0) out[0] = allGood ? total : kListFallback;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -356,6 +356,14 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
     const int N = static_cast<int>(cam.ommatidia.size());
     cs.N = N;
     if (static_cast<long long>(N) * cs.S >= (1ll << 31)) throw std::runtime_error("N*S must stay below 2^31 rays per frame");
+    if (cs.shardGlobalN > 0) {
+        // stream id = globalN*s + first + o must stay a valid subsequence index (the reference's id is an int,
+        // shaders.cu:668-669) and the shard must lie inside the eye, or ids collide across samples
+        if (cs.shardFirst + static_cast<uint64_t>(N) > cs.shardGlobalN)
+            throw std::runtime_error("crSetOmmatidialShard: firstIndex + ommatidia exceeds globalCount");
+        if (cs.shardGlobalN * static_cast<uint64_t>(cs.S) >= (1ull << 31))
+            throw std::runtime_error("crSetOmmatidialShard: globalCount * samples must stay below 2^31 sample streams");
+    }
     if (cs.ommDirty || !cs.dOmm) {
         dfree(cs.dOmm); dfree(cs.dPre);
         cs.dOmm = dallocT<float4>(2 * static_cast<size_t>(N));
@@ -367,6 +375,7 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
     }
     if (cs.rngN != N || cs.rngS != cs.S || !cs.dRng) {
         dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples);
+        cs.dLastSummed = nullptr;
         cs.dRng = dallocT<uint4>(2 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
         cs.dSamples = dallocT<float>(3 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
         cs.dSummed = dallocT<float4>(static_cast<size_t>(N));
@@ -386,7 +395,8 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
                       sharded ? cs.shardFirst : 0ull, dJumpTable_, stream_);
         launches_++;
         cs.frameIndex = cs.firstFrame;
-        cs.randomsConfigured = true;
+        cs.firstFrame = 0;                               // consumed: a later re-initialisation (new S, new count) restarts at frame 0,
+        cs.randomsConfigured = true;                     // as the reference's curand_init(42, id, 0) always does
     }
 }
 
@@ -408,7 +418,11 @@ void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
         cs.entryCap = need;
     }
     // candidate lists only where K1 can use them: whole warps per ommatidium (S % 32 == 0)
-    const bool wantLists = candidateLists && cs.S % 32 == 0;
+    // ... and where the second stage pays: it lengthens the frontier pass's latency chain, which a batch hides behind the
+    // previous frames' tracing but a single synchronous frame does not (measured on the headline workload: +1.7 % per
+    // batched frame, -3 % through renderFrame).  candidateLists: 0 never, 1 batches of >= 4 frames, 2 always.
+    const int framesNow = ep.poses ? ep.nFrames : 1;
+    const bool wantLists = cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && framesNow >= 4));
     if (wantLists && cs.listCap < need) {
         dfree(cs.dLists);
         cs.dLists = dallocT<int>(need * static_cast<size_t>(candidateListStride()));
@@ -472,6 +486,7 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;   // trace + ordered sum
     cs.frameIndex++;
+    cs.dLastSummed = cs.dSummed;
 }
 
 void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
@@ -498,6 +513,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;
     cs.frameIndex += static_cast<uint64_t>(nFrames);
+    cs.dLastSummed = dSummed + static_cast<size_t>(nFrames - 1) * static_cast<size_t>(cs.N);
 }
 
 void Renderer::project(CompoundState& cs, const HostCamera& cam)
@@ -639,9 +655,10 @@ void Renderer::copyOmmatidialData(float* outRgb)
 {
     if (!compoundActive() || !outRgb) return;
     CompoundState& cs = compoundState(current_);
-    if (!cs.dSummed) return;
+    const float4* src = cs.dLastSummed ? cs.dLastSummed : cs.dSummed;
+    if (!src) return;
     std::vector<float4> tmp(static_cast<size_t>(cs.N));
-    CR_CUDA(cudaMemcpyAsync(tmp.data(), cs.dSummed, sizeof(float4) * tmp.size(), cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaMemcpyAsync(tmp.data(), src, sizeof(float4) * tmp.size(), cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
     for (size_t i = 0; i < tmp.size(); i++) { outRgb[3 * i] = tmp[i].x; outRgb[3 * i + 1] = tmp[i].y; outRgb[3 * i + 2] = tmp[i].z; }
 }
@@ -685,6 +702,7 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
     }
     if (cs.batchSummedCap < F * N) {
         dfree(cs.dBatchSummed);
+        cs.dLastSummed = nullptr;
         cs.dBatchSummed = dallocT<float4>(F * N);
         CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
         cs.batchSummedCap = F * N;
@@ -694,7 +712,8 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         cs.dEntries = dallocT<int4>(F * N);
         cs.entryCap = F * N;
     }
-    if (entryFrontierActive(cs, static_cast<int>(F)) && candidateLists && cs.S % 32 == 0 && cs.listCap < F * N) {
+    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)) &&
+        cs.listCap < F * N) {
         dfree(cs.dLists);
         cs.dLists = dallocT<int>(F * N * static_cast<size_t>(candidateListStride()));
         cs.listCap = F * N;

@@ -23,6 +23,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     float4* dPre = nullptr;            // per-ommatidium ray invariants
     uint4* dRng = nullptr;
     float4* dSummed = nullptr;
+    const float4* dLastSummed = nullptr;   // per-ommatidium RGB of the most recent frame: dSummed, or the last row of a pose batch
     float* dSamples = nullptr;         // per-sample colour/S, [o][s]
     uint32_t* dMap = nullptr;          // cached pixel -> ommatidium map
     int mapMode = -2, mapW = 0, mapH = 0;
@@ -80,7 +81,7 @@ public:
     // Default: ordered sum + cr_math.h = every output bit equal to the CPU checker.
     bool fusedReduce = false;          // K1 sums 32 samples per warp in-kernel (fixed order, RGB equal to rounding) -- no sample buffer
     bool fastMath = false;             // hardware sin/cos/log/pow, as the reference's --use_fast_math build
-    int candidateLists = 1;            // 0: no per-ommatidium candidate lists (A/B switch, crDebugSetCandidateLists): per-lane walk only
+    int candidateLists = 1;            // per-ommatidium candidate lists: 0 never, 1 in batches of >= 4 frames (default), 2 always
     int width() const { return W_; }
     int height() const { return H_; }
 
@@ -88,6 +89,16 @@ public:
     void copyOmmatidialData(float* outRgb);                       // float RGB per ommatidium of the last frame
     double renderPoseBatch(const float* poses12, size_t count, unsigned char* outRgba, void* outDevice);
     static const std::vector<uint32_t>& xorwowTable();
+    // multi-GPU data plane (cr_comm.cpp): NCCL communicator of one process per GPU
+    void commUniqueId(void* out128);
+    void commInit(const void* id128, int nRanks, int rank);
+    void commDestroy();
+    int commRank() const { return commRank_; }
+    int commSize() const { return commSize_; }
+    int commNcclVersion();
+    void allGatherRows(const void* sendDevice, void* recvDevice, size_t bytesPerRank);
+    double renderPoseBatchSharded(const float* poses12, size_t count, unsigned char* outHost, void* outDevice, size_t chunkPoses,
+                                  uint64_t firstFrame);
     void setFirstFrame(uint64_t k);
     void setOmmatidialShard(uint64_t globalCount, uint64_t first);
     double lastTraceMs() { wantTraceEvents_ = true; return lastTraceMs_; }   // per-frame CUDA events only once somebody asks
@@ -158,6 +169,10 @@ private:
     bool frameWasFetched_ = true;                                 // the caller read the previous frame (getFramePointer/saveFrameAs)
     static constexpr size_t kEagerFrameBytes = size_t(1) << 20;
     int frameW_ = 0, frameH_ = 0;
+
+    void* comm_ = nullptr;                                        // ncclComm_t (cr_comm.cpp)
+    cudaStream_t commStream_ = nullptr;
+    int commRank_ = 0, commSize_ = 1;
 
     double lastTraceMs_ = 0.0;
     bool wantTraceEvents_ = false;                                // renderFrame records its event pair only after crGetLastTraceMs was used

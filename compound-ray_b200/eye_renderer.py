@@ -107,6 +107,11 @@ def configureFunctions(eyeRenderer):
     r.crRenderPoseBatch.restype = C.c_double
     r.crSetFirstFrame.argtypes = [C.c_uint64]
     r.crSetOmmatidialShard.argtypes = [C.c_uint64, C.c_uint64]
+    r.crCommGetUniqueId.argtypes = [vp]
+    r.crCommInit.argtypes = [vp, C.c_int, C.c_int]
+    r.crAllGatherRows.argtypes = [vp, vp, C.c_size_t]
+    r.crRenderPoseBatchSharded.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, C.c_uint64]
+    r.crRenderPoseBatchSharded.restype = C.c_double
     r.crSetRenderMode.argtypes = [C.c_int, C.c_int]
     r.crGetRenderMode.restype = C.c_int
     r.crDebugSetCandidateLists.argtypes = [C.c_int]

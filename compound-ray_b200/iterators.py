@@ -5,9 +5,13 @@ Same classes, constructor arguments and yielded tuples as the reference's ``Rand
 ``UniformCubeIterator``; the difference is inside: instead of one ``setCameraPosition`` +
 ``renderFrame`` + ``getFramePointer`` round trip per item, blocks of poses are rendered by
 ``crRenderPoseBatch`` (several frames per kernel launch, one device->host copy per block) and handed
-out one by one.  Frame k of the iterator is still frame k of every RNG stream, so the images are
-byte-identical to the reference loop's.  ``RandomCubeIterator`` draws positions from numpy's global
-RNG exactly as the reference does (``np.random.random(3)`` per item, in order).
+out one by one.  Item k of the iterator is frame k of every RNG stream, so the images are byte-identical to
+the reference loop's: a block that is abandoned part-way (``iter()`` called again, an epoch that ends inside a
+block) rewinds the streams to the number of items actually handed out (``crSetFirstFrame``) before the next
+block is rendered.  ``RandomCubeIterator`` draws positions from numpy's global RNG exactly as the reference does
+(``np.random.random(3)`` per item, in order) but ``blockSize`` items AHEAD of the item it returns: code that
+interleaves its own ``np.random`` calls with ``next()`` sees a different global sequence than with the reference
+loop (use ``blockSize=1`` there).
 """
 from __future__ import annotations
 
@@ -43,9 +47,16 @@ class CompoundRayIterator:
         self._rows = None
         self._positions = None
         self._cursor = 0
+        self._consumed = 0          # items handed out since the streams were initialised = the frame the next item must be
 
     def __iter__(self):
         return self
+
+    def _drop_block(self):
+        """Forget a block whose tail was rendered but never handed out: the streams go back to frame `_consumed`."""
+        if self._rows is not None and self._cursor < len(self._rows):
+            self.eyeRenderer.crSetFirstFrame(int(self._consumed))
+        self._rows = None
 
     def _render_block(self, positions):
         poses = er.make_poses(positions, x=self._axes[0:3], y=self._axes[3:6], z=self._axes[6:9])
@@ -72,6 +83,7 @@ class RandomCubeIterator(CompoundRayIterator):
             self._render_block(rel)
         i = self._cursor
         self._cursor += 1
+        self._consumed += 1
         image = np.copy(self._rows[i][:, :, :3])
         return torch.from_numpy(image.astype(np.dtype("f"))), torch.from_numpy(self._positions[i].astype(np.dtype("f")))
 
@@ -89,7 +101,7 @@ class UniformCubeIterator(CompoundRayIterator):
         self.sampleID = 0
         self.sampleGap = self.cubeSize / (self.samplingSize + 1)
         self.startPos = np.ones(3) * (-(self.samplingSize * self.sampleGap) / 2)
-        self._rows = None
+        self._drop_block()
         return self
 
     def _coord(self, sid):
@@ -109,6 +121,7 @@ class UniformCubeIterator(CompoundRayIterator):
             self._render_block(pos)
         i = self._cursor
         self._cursor += 1
+        self._consumed += 1
         self.sampleID = (self.sampleID + 1) % total
         coord = self._coords[i]
         samplingPos = self._positions[i]

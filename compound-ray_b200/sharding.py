@@ -66,6 +66,10 @@ class ChunkedPoseGather:
         row_shape = tuple(row_shape)
         self.send = torch.zeros((self.blk,) + row_shape, dtype=dtype, device=device)
         self.gathered = torch.zeros((world, self.blk) + row_shape, dtype=dtype, device=device)
+        # The library writes rows into `send` from its OWN non-blocking stream, which is not ordered against torch's
+        # current stream: the zero-fills above must have finished before the first crRenderPoseBatch is issued.
+        if self.send.is_cuda:
+            torch.cuda.current_stream(self.send.device).synchronize()
         chunk = max(1, int(chunk))
         self.chunks = [(c0, min(c0 + chunk, self.blk)) for c0 in range(0, self.blk, chunk)]
         self.handles = []
@@ -129,3 +133,58 @@ def allgather_rows(local_rows, world: int, n_total: int, dist=None):
     gathered = torch.zeros((world * blk,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
     return unpad(gathered, world, n_total)
+
+
+# ---------------------------------------------------------------------------------------------
+# The library's own data plane (csrc/cr_comm.cpp): ncclAllGather / grouped ncclBroadcast issued by the C++ host.
+# Python only carries the 128-byte NCCL unique id from rank 0 to the other ranks.
+# ---------------------------------------------------------------------------------------------
+def init_library_comm(lib, rank: int, world: int, dist=None, id_path: str | None = None) -> None:
+    """crCommInit on every rank.  The unique id travels over an existing torch.distributed group (`dist`, any backend:
+    the bytes are broadcast as a CPU or CUDA tensor) or, without torch, through the file `id_path`."""
+    import ctypes as C
+    import numpy as np
+    buf = np.zeros(128, np.uint8)
+    if rank == 0:
+        if lib.crCommGetUniqueId(buf.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("crCommGetUniqueId failed (NCCL not loadable?)")
+    if world > 1:
+        if dist is not None:
+            import torch
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.from_numpy(buf).to(dev)
+            dist.broadcast(t, src=0)
+            buf = t.cpu().numpy().copy()
+        elif id_path is not None:
+            import os
+            import time
+            if rank == 0:
+                with open(id_path + ".tmp", "wb") as f:
+                    f.write(buf.tobytes())
+                os.replace(id_path + ".tmp", id_path)
+            else:
+                for _ in range(6000):
+                    if os.path.exists(id_path):
+                        break
+                    time.sleep(0.01)
+                buf = np.frombuffer(open(id_path, "rb").read(), np.uint8).copy()
+        else:
+            raise ValueError("world > 1 needs a torch.distributed group or an id file")
+    if lib.crCommInit(buf.ctypes.data_as(C.c_void_p), int(world), int(rank)) != 0:
+        raise RuntimeError("crCommInit failed")
+
+
+def render_pose_batch_sharded(lib, poses, chunk: int = 0, first_frame: int = 0, out_device_ptr=None):
+    """crRenderPoseBatchSharded: every rank passes the same [P][12] poses and gets all P rows (uint8[P][N][4]) back."""
+    import ctypes as C
+    import numpy as np
+    poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 12)
+    n = lib.getCurrentEyeOmmatidialCount()
+    if out_device_ptr is not None:
+        ms = lib.crRenderPoseBatchSharded(poses.ctypes.data_as(C.c_void_p), len(poses), None, C.c_void_p(out_device_ptr), int(chunk), int(first_frame))
+        return None, ms
+    out = np.zeros((len(poses), n, 4), dtype=np.uint8)
+    ms = lib.crRenderPoseBatchSharded(poses.ctypes.data_as(C.c_void_p), len(poses), out.ctypes.data_as(C.c_void_p), None, int(chunk), int(first_frame))
+    if ms < 0:
+        raise RuntimeError("crRenderPoseBatchSharded failed")
+    return out, ms

@@ -101,14 +101,47 @@ void crGetOmmatidialData(float* outRgb);
  * (4 bytes per ommatidium).  outDevice (a CUDA device pointer) takes precedence over outHost.
  * Returns host-timed milliseconds. */
 double crRenderPoseBatch(const float* poses, size_t count, unsigned char* outHost, void* outDevice);
+/* outDevice is written from the library's own (non-blocking) CUDA stream and the call returns after that stream is idle:
+ * the buffer must not have work pending on any other stream when the call is made (e.g. a torch.zeros fill still
+ * queued on torch's stream -- synchronise that stream first), and may be read from any stream once the call returned.
+ * crGetOmmatidialData after this call returns the float RGB of the LAST pose of the batch. */
 /* Position the RNG streams as if `frame` frames had already been rendered (pose sharding/restart);
- * takes effect at the next stream initialisation, which this call forces. */
+ * takes effect at the next stream initialisation, which this call forces, and is consumed by it: any LATER
+ * re-initialisation (setCurrentEyeSamplesPerOmmatidium, setOmmatidia with a new count, crSetOmmatidialShard) restarts
+ * at frame 0 as the reference does. */
 void crSetFirstFrame(uint64_t frame);
 /* Ommatidium-range sharding (one pose, large N*S; SURVEY 8e secondary partition): declare that the rows given to
  * setOmmatidia are rows [firstIndex, firstIndex+count) of an eye of globalCount ommatidia.  Sample stream ids then
  * use the global indices (id = globalCount*s + firstIndex + o, shaders.cu:680-685), so the gathered per-ommatidium
- * results equal the unsharded frame bit for bit.  globalCount = 0 switches back.  Forces a stream initialisation. */
+ * results equal the unsharded frame bit for bit.  globalCount = 0 switches back.  Forces a stream initialisation.
+ * The next render fails (logged, nothing drawn) unless firstIndex + count <= globalCount and globalCount * S < 2^31. */
 void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex);
+/* ---- multi-GPU data plane: one process per GPU, NCCL all-gather of the per-pose rows, owned by the library.
+ * NCCL is bound at run time (libnccl.so.2 -- a copy already loaded into the process, e.g. torch's, is reused; CR_NCCL_LIB
+ * overrides), so nothing here is needed, or loaded, for single-GPU use.  Functions returning int give 0 on success, -1 on
+ * failure (logged).  The reference has no counterpart: its scripts render on one GPU. */
+/* Rank 0: fills the 128-byte NCCL unique id, which the launcher passes to every rank by its own means (MPI,
+ * torch.distributed broadcast, a file). */
+int crCommGetUniqueId(void* out128);
+/* Every rank, collectively: joins the communicator on the library's device (crSetDevice first). */
+int crCommInit(const void* id128, int nRanks, int rank);
+void crCommDestroy(void);
+int crCommRank(void);                 /* 0 without a communicator */
+int crCommSize(void);                 /* 1 without a communicator */
+int crCommNcclVersion(void);          /* e.g. 22809; 0 when NCCL cannot be loaded */
+/* recvDevice[q * bytesPerRank ...] := rank q's sendDevice on every rank (ncclAllGather on the library's communication
+ * stream; sendDevice may be the rank's own slot of recvDevice).  Returns when recvDevice is complete.  Use after
+ * crRenderPoseBatch(..., outDevice = send slot) for ommatidium-range or hand-made pose shards. */
+int crAllGatherRows(const void* sendDevice, void* recvDevice, size_t bytesPerRank);
+/* One logical `count`-pose run over all ranks of the communicator (or this GPU alone without one).  Every rank passes the
+ * SAME poses (12 floats each); rank r renders the contiguous block [r*count/R ...) with its sample streams positioned at
+ * firstFrame + its first pose, so pose k is frame firstFrame + k of every stream for ANY number of ranks and the result
+ * does not depend on R.  The block is rendered in chunks of chunkPoses poses (0 = one chunk); each chunk's rows are
+ * gathered into their final places on the communication stream while the next chunk is traced.  Every rank receives all
+ * count*N*4 bytes, in pose order, in outDevice (device memory) and/or outHost.  Returns host milliseconds (-1 on failure);
+ * crGetLastTraceMs then gives the device time of this rank's trace launches. */
+double crRenderPoseBatchSharded(const float* poses, size_t count, unsigned char* outHost, void* outDevice, size_t chunkPoses,
+                                uint64_t firstFrame);
 /* Render modes of the compound path; a negative argument leaves that switch as it is.  Both default to 0 (also preset by
  * the environment variables CR_REDUCE=fused and CR_FAST_MATH=1, for scripts that cannot call this).
  *   fusedReduction 0: every sample's colour/S is stored and summed in sample order -- the reference's sequential fp32
@@ -162,10 +195,11 @@ void crDebugSetRayDump(bool on);
 /* A/B switch of the per-ommatidium entry frontier (default: on for S >= 8 and N*S >= 786432 rays per frame);
  * negative thresholds keep the current value. */
 void crDebugSetEntryFrontier(int on, int minSamples, long long minRaysPerFrame);
-/* A/B switch of the per-ommatidium candidate lists (default on; they need the entry frontier and S % 32 == 0): the
- * frontier pass also flattens what an ommatidium's sample cone can reach into a list of <= 15 pre-leaf BVH nodes, which
- * the 32 samples a warp holds of that ommatidium test in lockstep instead of walking the tree per lane.  The closest
- * hit is the same either way. */
+/* Switch of the per-ommatidium candidate lists (they need the entry frontier and S % 32 == 0): the frontier pass also
+ * flattens what an ommatidium's sample cone can reach into a list of <= 15 pre-leaf BVH nodes, which the 32 samples a warp
+ * holds of that ommatidium test in lockstep instead of walking the tree per lane.  0 = never, 1 = in launches that cover
+ * at least 4 frames (default: the extra latency of building them hides behind a batch, not behind one synchronous frame),
+ * 2 = always.  The closest hit is the same either way. */
 void crDebugSetCandidateLists(int on);
 /* The candidate lists of the last trace launch: 16 ints per (frame, ommatidium) -- [0] = element count (-1: none, the
  * frontier is walked per lane; 0: the cone reaches no leaf), [1..] = node << 2 | reachable-leaf mask.  Returns the

@@ -75,6 +75,8 @@ def lib(er):
     # The parity tests use small frames; by default those skip the entry-frontier pass (it only pays above
     # ~0.5M rays per frame).  Force it on for S >= 2 so every oracle comparison also exercises that path.
     L.crDebugSetEntryFrontier(1, 2, 0)
+    # ... and the per-ommatidium candidate lists, which by default are only built in batches of >= 4 frames
+    L.crDebugSetCandidateLists(2)
     return L
 
 

@@ -1,9 +1,10 @@
 """tests/golden/make_fixtures.py -- regenerates the committed fixtures (run in the dev container,
 where /root/reference and the CUDA toolkit exist; the GPU box has neither the reference tree).
 
-  reference_data.tar.gz  INPUT DATA only (scenes + .eye tables) packed from the reference's data
-                         directories, so the parity tests can run on the reference's own scenes on
-                         a box without /root/reference.  No reference source code is included.
+  reference_data.tar.gz  INPUT DATA (scenes + .eye tables) packed from the reference's data directories, so the
+                         parity tests can run on the reference's own scenes on a box without /root/reference --
+                         plus, as acceptance fixtures, the reference's ctypes helper and two example scripts, which
+                         tests/test_gpu_scripts.py runs unmodified against this library.
   xorwow_kat.json        cuRAND's own host XORWOW implementation (oracle/_ref/curand_kat)
   sutil_kat.json         the reference's sutil math headers evaluated on fixed inputs (oracle/_ref/sutil_kat)
   hitscan_kat.json       the reference's sutil/hitscanprocessing.cpp (point-in-hitbox, bounds) on three meshes x 400 points
@@ -43,6 +44,13 @@ FILES = {
     "data/eyes/1000-horizontallyAcute-variableDegree.eye": "data/eyes/1000-horizontallyAcute-variableDegree.eye",
     "sim-environment/env_2.gltf": TOY + "/env_2.gltf",
     "sim-environment/eyes/AM_60185-real.eye": TOY + "/eyes/AM_60185-real.eye",
+    # The reference's own ctypes helper and two of its example scripts, as ACCEPTANCE FIXTURES: tests/test_gpu_scripts.py
+    # runs them UNMODIFIED (byte for byte as packed here) against this library -- the drop-in claim of INTEGRATION.md.
+    # They are test inputs, never imported by the product.
+    "python-examples/eyeRendererHelperFunctions.py": "python-examples/eyeRendererHelperFunctions.py",
+    "python-examples/primary-example.py": "python-examples/primary-example.py",
+    "python-examples/position-estimation-toy-experiment/compoundRayIterators.py":
+        "python-examples/position-estimation-toy-experiment/compoundRayIterators.py",
 }
 
 

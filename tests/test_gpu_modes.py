@@ -33,7 +33,7 @@ def terrain(synth_dir):
 def _default_modes(lib):
     yield
     lib.crSetRenderMode(0, 0)
-    lib.crDebugSetCandidateLists(1)
+    lib.crDebugSetCandidateLists(2)
     lib.crDebugSetRayDump(False)
     lib.crDebugSetEntryFrontier(1, 2, 0)
     lib.crSetFirstFrame(0)
@@ -70,7 +70,7 @@ def test_candidate_lists_equal_per_lane_walk_and_oracle(lib, er, loader, oracle,
     eye.render_frame(method="bvh")                               # frame 1: the cached Box-Muller half is in play
     res = {}
     for lists, frontier in ((0, 1), (1, 1), (0, 0)):
-        lib.crDebugSetCandidateLists(lists)
+        lib.crDebugSetCandidateLists(2 * lists)
         lib.crDebugSetEntryFrontier(frontier, 2, 0)
         lib.setCurrentEyeSamplesPerOmmatidium(S)                 # restart the streams
         lib.crDebugSetRayDump(True)
@@ -91,7 +91,7 @@ def test_candidate_lists_equal_per_lane_walk_and_oracle(lib, er, loader, oracle,
     assert n_root[0] > 1.5 * n_walk[0]
     assert not np.array_equal(walk[3], listed[3]), "the candidate lists were not used"
     # structure of the lists of the last frame: header in {-1, 0..15}; elements name internal nodes and a non-empty leaf mask
-    lib.crDebugSetCandidateLists(1)
+    lib.crDebugSetCandidateLists(2)
     lib.crDebugSetEntryFrontier(1, 2, 0)
     lib.renderFrame()
     rec = np.zeros((N, 16), np.int32)
@@ -142,7 +142,7 @@ def test_candidate_lists_stress_eye_and_batches(lib, er, terrain):
     poses = np.asarray(poses, np.float32)
     res = {}
     for lists in (0, 1):
-        lib.crDebugSetCandidateLists(lists)
+        lib.crDebugSetCandidateLists(2 * lists)
         lib.setCurrentEyeSamplesPerOmmatidium(S)
         lib.crDebugSetRayDump(True)
         frames = []
