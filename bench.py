@@ -151,18 +151,20 @@ def poses_for(cam_pos, axes, count, first_index):
 
 def traversal_counters(lib, er, S_probe=32):
     """Per-ray BVH nodes fetched / triangles tested, counted ON THE DEVICE by the dump variant of the trace
-    kernel (same code path: entry frontier and warp packets included; a lane counts a node only when its own ray
-    reached it) on a probe frame of S_probe samples, plus the same figures for a plain root-to-leaf walk counted by
+    kernel (same code path: entry frontier and candidate lists included -- a listed ray counts every element of its
+    ommatidium's list as a node fetch) on a probe frame of S_probe samples, plus the same figures for a plain root-to-leaf walk counted by
     the CPU oracle's instrumented traversal of the IDENTICAL device BVH on the product's own rays (which also
     re-checks the hit ids)."""
     from oracle import oracle as O
     N = lib.getCurrentEyeOmmatidialCount()
     S_keep = lib.getCurrentEyeSamplesPerOmmatidium()
     lib.setCurrentEyeSamplesPerOmmatidium(S_probe)
-    lib.crDebugSetEntryFrontier(1, -1, 0)            # the probe frame is small: keep the frontier pass of the timed frames
+    lib.crDebugSetEntryFrontier(1, -1, 0)            # the probe frame is small and single: keep the frontier pass and the
+    lib.crDebugSetCandidateLists(2)                  # candidate lists of the timed (batched) frames
     lib.crDebugSetRayDump(True)
     lib.renderFrame()
     lib.crDebugSetEntryFrontier(1, -1, 3 << 18)
+    lib.crDebugSetCandidateLists(1)
     n = N * S_probe
     o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); h = np.zeros((n, 4), np.int32)
     lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data)
@@ -383,24 +385,34 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()                                       # sampled from warm-up to the end of the e2e loop
 
-    def timed_batches(first_frame, repeats, with_gather=True):
+    # Every timed batch, on every rank, renders the SAME K camera poses (a new pose every frame within the batch): the
+    # per-rank work of this weak-scaling run is then identical by construction, not just statistically, and the scaling
+    # figure measures the machine, not the luck of a rank's pose draw (pose sets differ by +-3 % in cost).  The sample
+    # streams do advance from batch to batch and differ between ranks (crSetFirstFrame), so no two batches trace the same rays.
+    timed_poses = poses_for(cam_pos, axes, K, W)
+    rank_ms = []                                          # per batch: (this rank's trace ms, this rank's gather ms)
+
+    def timed_batches(repeats, with_gather=True):
         """`repeats` batches of K frames; per batch: barrier + sync, CUDA events around the fused launches on the library
         stream (+ torch events around ncclAllGather), max over ranks."""
         out = []
         for b in range(repeats):
-            timed = poses_for(cam_pos, axes, K, first_frame + b * K)
+            timed = timed_poses
             if world > 1:
                 dist.barrier()
                 torch.cuda.synchronize()
                 er.renderPoseBatch(lib, timed, out_device_ptr=out_dev)       # returns after the stream is idle
                 dev_ms = lib.crGetLastTraceMs()
+                g_ms = 0.0
                 if with_gather:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
                     e1.record()
                     torch.cuda.synchronize()
-                    dev_ms += e0.elapsed_time(e1)
+                    g_ms = e0.elapsed_time(e1)
+                rank_ms.append((dev_ms, g_ms))
+                dev_ms += g_ms
                 t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dev_ms = float(t.item())
@@ -412,14 +424,14 @@ def main():
 
     er.renderPoseBatch(lib, poses_for(cam_pos, axes, W, first), out_device_ptr=None)   # W untimed warm-up frames (incl. RNG init)
     if world > 1:                                         # ... and the collective with its real shape (first call builds channels)
-        er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, first + W), out_device_ptr=out_dev)
+        er.renderPoseBatch(lib, timed_poses, out_device_ptr=out_dev)
         for _ in range(2):
             dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
         torch.cuda.synchronize()
     else:
-        er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, first + W))      # same shape as the timed batches (allocations)
+        er.renderPoseBatch(lib, timed_poses)                                  # same shape as the timed batches (allocations)
     launches1 = lib.crGetLaunchCount()
-    batch_ms = timed_batches(first + W + K, R)
+    batch_ms = timed_batches(R)
     launches_timed = lib.crGetLaunchCount() - launches1
     frames_per_launch = int(lib.crGetLastBatchFrames())
     dev_ms = float(np.median(batch_ms))
@@ -460,7 +472,7 @@ def main():
             lib.crSetRenderMode(*MODES[name])
             lib.setCurrentEyeSamplesPerOmmatidium(S)
             er.renderPoseBatch(lib, poses_for(cam_pos, axes, K, 0))
-            ms = float(np.median(timed_batches(K, 3)))
+            ms = float(np.median(timed_batches(3)))
             es = e2e_run(Ke, 4 * K)
             modes[name] = {"rays_per_sec": K * rays_per_step / (ms * 1e-3), "e2e_rays_per_sec": Ke * rays_per_step / es,
                            "frames_per_launch": int(lib.crGetLastBatchFrames())}
@@ -470,6 +482,13 @@ def main():
         lib.crSetRenderMode(*MODES[args.mode])
         lib.setCurrentEyeSamplesPerOmmatidium(S)
     clocks = sampler.stop()
+    per_rank = None
+    if world > 1:                                         # diagnostics: every rank's median trace time and gather time (incl. waiting)
+        mine = torch.tensor([float(np.median([a for a, _ in rank_ms[:R]])), float(np.median([g for _, g in rank_ms[:R]]))],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"trace_ms_per_batch": [float(t[0]) for t in allr], "gather_ms_per_batch_incl_wait": [float(t[1]) for t in allr]}
 
     out = None
     if rank == 0:
@@ -524,7 +543,7 @@ def main():
                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": dict(workload_config(args), mode=args.mode), "clocks": clocks, "e2e": e2e,
                "gpu_launches": int(launches_timed), "gpu_launches_per_batch": int(launches_timed) // R,
-               "repeats": R, "batch_ms": batch_ms, "roofline": roofline, "cpu_baseline": cpu, "modes": modes,
+               "repeats": R, "batch_ms": batch_ms, "per_rank": per_rank, "roofline": roofline, "cpu_baseline": cpu, "modes": modes,
                "ommatidia_frames_per_sec": value / S, "bvh_build_ms": lib.crGetBvhBuildMs(),
                "timing": f"median of {R} batches of {K} frames; CUDA events around each batch's fused trace+reduce launches on the "
                          "library stream" + (", plus torch events around ncclAllGather of the batch's rows; max over ranks per batch"

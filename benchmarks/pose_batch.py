@@ -73,14 +73,27 @@ def main():
     if args.native:
         sharding.init_library_comm(lib, rank, world, dist if use_torch else None, args.id_file)
         sharding.render_pose_batch_sharded(lib, all_poses[:min(8 * world, P)], chunk=args.chunk)      # warm-up incl. the collective
+        dev_out = None
+        try:                                        # result stays in device memory on every rank, as in the torch legs below
+            import torch
+            torch.cuda.set_device(local)
+            dev_out = torch.empty((P, N, 4), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        if use_torch:
+            dist.barrier()
         t0 = time.perf_counter()
-        rows, _ = sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk)     # all P rows on every rank, host side
+        if dev_out is not None:
+            sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk, out_device_ptr=dev_out.data_ptr())
+        else:
+            rows, _ = sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk)   # all P rows on every rank, host side
         dt = time.perf_counter() - t0
         if use_torch:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        checksum = int(rows.astype(np.int64).sum())
+        checksum = int(dev_out.to(torch.int64).sum().item()) if dev_out is not None else int(rows.astype(np.int64).sum())
         lib.crCommDestroy()
     elif args.chunk > 0:
         import torch
@@ -121,15 +134,25 @@ def main():
         dt = float(t.item())
         checksum = int(sharding.unpad(gathered, world, P).to(torch.int64).sum().item())
     else:
-        t0 = time.perf_counter()
-        rows, _ = er.renderPoseBatch(lib, poses)
-        dt = time.perf_counter() - t0
-        checksum = int(rows.astype(np.int64).sum())
+        try:                                        # as the multi-GPU legs: the rows stay in device memory
+            import torch
+            torch.cuda.set_device(local)
+            dev_out = torch.empty((P, N, 4), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            er.renderPoseBatch(lib, poses, out_device_ptr=dev_out.data_ptr())
+            dt = time.perf_counter() - t0
+            checksum = int(dev_out.to(torch.int64).sum().item())
+        except ImportError:
+            t0 = time.perf_counter()
+            rows, _ = er.renderPoseBatch(lib, poses)
+            dt = time.perf_counter() - t0
+            checksum = int(rows.astype(np.int64).sum())
     if rank == 0:
         out = {"benchmark": "pose batch (BASELINE config 5)", "n_gpus": world, "poses": P, "ommatidia": N, "samples": S,
                "chunk": args.chunk, "mode": args.mode,
                "data_plane": "library (crRenderPoseBatchSharded: ncclBroadcast groups per chunk, C++)" if args.native else "torch.distributed", "seconds": dt, "poses_per_sec": P / dt, "rays_per_sec": P * N * S / dt, "ommatidia_frames_per_sec": P * N / dt,
-               "checksum": checksum, "timing": "host wall clock incl. pose upload, render, allgather / D2H; max over ranks"}
+               "checksum": checksum, "timing": "host wall clock incl. pose upload, render and gather; every rank ends with all rows in DEVICE memory; max over ranks"}
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if use_torch:
         dist.destroy_process_group()

@@ -27,6 +27,8 @@
 //             r[0] = (d, v0, v1, v2)   r[1] = (v3, v4, boxmuller_flag, boxmuller_extra bits)
 //   samples float[3*N*S]       per-sample colour/S, laid out [o][s] (12 B per ray, written by K1; ordered mode)
 //   partials float4[N*S/32]    fused mode instead: one butterfly sum of 32 samples per warp (0.5 B per ray)
+//   queue   float4[2*cap] + int4[cap]   wavefront queue (batches): rays of the ommatidia without a candidate list, traced by
+//                              k_traceQueue with dynamic ray fetch and shaded by k_shadeQueue (48 B per queued ray)
 //   summed  float4[N]          per-ommatidium RGB: sequential sum of the samples (K1b)
 #pragma once
 #include <cuda_runtime.h>
@@ -80,6 +82,11 @@ struct EyeParams {
     uchar4* fastRow = nullptr;           // when set: K1b also writes make_color(summed[i]) for i < fastRowCount
     int fastRowCount = 0;
     const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
+    // wavefront queue of the warp-frames whose ommatidium has no candidate list (k_traceCompound -> k_traceQueue -> k_shadeQueue)
+    float4* queueRays = nullptr;         // 2 float4 per ray: (origin, tmin), (direction, id = frame*N*S + r | inCone << 31)
+    int4* queueHits = nullptr;           // (prim, t bits, u bits, v bits) per queued ray
+    unsigned* queueCounters = nullptr;   // [0] rays pushed by K1 (multiples of 32), [1] rays handed out by k_traceQueue
+    unsigned queueCap = 0;               // rays the queue holds; a warp that finds it full walks inline
     float4* partials = nullptr;          // fused reduction: [nFrames][N][S/32] per-warp sums of 32 samples (K1 -> k_sumPartials)
     const int* lists = nullptr;          // [nFrames][N][16] candidate lists (k_buildEntries stage 2): header = element count, -1 = none
     bool fused = false;                  // in-kernel reduction (needs S % 32 == 0) instead of the ordered per-sample buffer

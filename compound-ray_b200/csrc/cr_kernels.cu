@@ -871,13 +871,39 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 listN = __ldg(list);
                 if (listN != kListFallback && !__all_sync(kFullMask, inCone)) listN = kListFallback;
             }
+            bool queued = false;
             if (listN != kListFallback) {
                 h = traceList<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, sWarp, lane, &nNode, &nTri, list, listN);
             } else {
-                int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
-                if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
-                h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
-                                       &nNode, &nTri, entry);
+                // No list: this warp-frame's 32 rays walk the BVH one by one -- the walk whose lanes drift apart.  In batches
+                // the whole warp-frame goes to the wavefront queue instead (k_traceQueue refills finished lanes with new
+                // rays; k_shadeQueue shades and reduces in this warp's lane order, so the result bits do not change).
+                if (!DUMP && ep.queueRays != nullptr && list != nullptr) {             // warp-uniform
+                    unsigned base = 0u;
+                    if (lane == 0) base = atomicAdd(ep.queueCounters, 32u);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (base + 32u <= ep.queueCap) {
+                        const unsigned slot = base + (unsigned)lane;
+                        const unsigned id = ((unsigned)f * total + r) | (inCone ? 0x80000000u : 0u);
+                        __stcs(ep.queueRays + 2 * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, ray.tmin));
+                        __stcs(ep.queueRays + 2 * (size_t)slot + 1, make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(id)));
+                        queued = true;
+                    }
+                }
+                if (!queued) {
+                    int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
+                    if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+                    h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
+                                           &nNode, &nTri, entry);
+                }
+            }
+            if (queued) {                                   // (warp-uniform) shaded and reduced by k_shadeQueue
+                if (MULTI) {
+                    const uint4 a = sRng[0][threadIdx.x], b = sRng[1][threadIdx.x];
+                    rng.d = a.x; rng.v0 = a.y; rng.v1 = a.z; rng.v2 = a.w; rng.v3 = b.x; rng.v4 = b.y;
+                    rng.flag = (int)b.z; rng.extra = __uint_as_float(b.w);
+                }
+                continue;
             }
             const V3 col = (h.prim >= 0) ? shadeHit<FAST>(sc, h) : shadeMiss<FAST>(sc.missShader, ray.d);
             float cx = col.x * invS, cy = col.y * invS, cz = col.z * invS;                       // shaders.cu:730
@@ -912,6 +938,155 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
             }
         }
         if (MULTI) rngStore(statePtr, rng);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Wavefront queue (batches).  K1 pushes the warp-frames it would have walked per lane; k_traceQueue traces them with
+// DYNAMIC RAY FETCH: persistent warps whose lanes pull the next ray of the queue as soon as their own is finished (checked
+// after every leaf round, refilled when fewer than kRefillBelow lanes are busy), so the node loop stays populated however
+// unequal the walks are -- the grazing ommatidia this path exists for visit 5 to 60 nodes per ray.  The closest hit does
+// not depend on which lane or kernel finds it (same box test, same triangle test, lowest-primitive tie rule), and
+// k_shadeQueue turns hits into colours and sums them warp-frame by warp-frame in K1's lane order: same output bits.
+// ------------------------------------------------------------------------------------------
+#ifndef CR_REFILL_BELOW
+#define CR_REFILL_BELOW 24
+#endif
+constexpr int kRefillBelow = CR_REFILL_BELOW;
+
+__global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceQueue(const DeviceScene sc, const EyeParams ep)
+{
+    __shared__ int sStack[kSmemStack][kTraceThreads];
+    const unsigned n = min(ep.queueCounters[0], ep.queueCap & ~31u);
+    const int lane = (int)(threadIdx.x & 31u);
+    const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
+    Stack st;
+    st.smem = &sStack[0][threadIdx.x]; st.stride = kTraceThreads; st.sp = 0;
+    RayBox rb;
+    rb.nix = rb.niy = rb.niz = rb.fix = rb.fiy = rb.fiz = rb.nax = rb.nay = rb.naz = rb.fax = rb.fay = rb.faz = 0.0f;
+    V3 ro = mk(0.0f, 0.0f, 0.0f), rd = mk(0.0f, 0.0f, 1.0f);
+    float tmin = 0.0f;
+    const float4* __restrict__ nodes = sc.nodes;
+    Hit best;
+    best.t = kTMax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+    int cur = kSentinel;
+    unsigned slot = 0u;
+    bool active = false, exhausted = false;
+    for (;;) {
+        if (!exhausted) {                                             // ---- refill the idle lanes
+            const unsigned need = __ballot_sync(kFullMask, !active);
+            if (need != 0u) {
+                const int leader = __ffs((int)need) - 1;
+                unsigned base = 0u;
+                if (lane == leader) base = atomicAdd(ep.queueCounters + 1, (unsigned)__popc(need));
+                base = __shfl_sync(kFullMask, base, leader);
+                if (base + (unsigned)__popc(need) >= n) exhausted = true;
+                const unsigned my = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                if (!active && my < n) {
+                    const float4 q0 = __ldcs(ep.queueRays + 2 * (size_t)my), q1 = __ldcs(ep.queueRays + 2 * (size_t)my + 1);
+                    ro = mk(q0.x, q0.y, q0.z); tmin = q0.w; rd = mk(q1.x, q1.y, q1.z);
+                    const unsigned idw = __float_as_uint(q1.w);
+                    int sx, sy, sz;
+                    setupAxis(ro.x, rd.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
+                    setupAxis(ro.y, rd.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
+                    setupAxis(ro.z, rd.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
+                    nodes = sc.nodes + (size_t)(sx | (sy << 1) | (sz << 2)) * sc.nodeVariantStride;
+                    best.t = kTMax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+                    st.sp = 0;
+                    int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
+                    if (ep.entries != nullptr && (idw & 0x80000000u)) {
+                        const unsigned id = idw & 0x7fffffffu;
+                        const unsigned f = id / total, o = (id - f * total) / (unsigned)ep.S;
+                        entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+                    }
+                    cur = entry.x;
+                    if (entry.y != kSentinel) {
+                        if (entry.z != kSentinel) {
+                            if (entry.w != kSentinel) st.push(entry.w);
+                            st.push(entry.z);
+                        }
+                        st.push(entry.y);
+                    }
+                    slot = my;
+                    active = true;
+                }
+            }
+        }
+        if (__ballot_sync(kFullMask, active) == 0u) break;
+        for (;;) {                                                    // ---- walk; leave to refill when the warp thins out
+            while (cur >= 0) {
+                const float4* np = nodes + 4 * (size_t)cur;
+                float4 n0, n1, n2, n3;
+                ldgNode(np, n0, n1, n2, n3);
+                const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), tmin));
+                const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), best.t));
+                const float tn1 = fmax3(fmaf(n1.x, rb.nix, rb.nax), fmaf(n1.z, rb.niy, rb.nay), fmaxf(fmaf(n2.z, rb.niz, rb.naz), tmin));
+                const float tf1 = fmin3(fmaf(n1.y, rb.fix, rb.fax), fmaf(n1.w, rb.fiy, rb.fay), fminf(fmaf(n2.w, rb.fiz, rb.faz), best.t));
+                const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
+                const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    const bool firstIs0 = tn0 <= tn1;
+                    cur = firstIs0 ? r0 : r1;
+                    st.push(firstIs0 ? r1 : r0);
+                } else if (h0) cur = r0;
+                else if (h1) cur = r1;
+                else cur = st.pop();
+            }
+            if (cur != kSentinel) {
+                const int x = ~cur;
+                const int first = x >> 3, cnt = (x & 7) + 1;
+                for (int k = 0; k < cnt; k++) {
+                    float t, u, v;
+                    int prim;
+                    if (triTest(sc.tris + 3 * (size_t)(first + k), ro, rd, tmin, best.t, t, u, v, prim)) {
+                        if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
+                    }
+                }
+                cur = st.pop();
+            }
+            if (active && cur == kSentinel) {
+                __stcs(ep.queueHits + slot, make_int4(best.prim, __float_as_int(best.t), __float_as_int(best.u), __float_as_int(best.v)));
+                active = false;
+            }
+            const unsigned live = __ballot_sync(kFullMask, active);
+            if (live == 0u || (!exhausted && __popc(live) < kRefillBelow)) break;
+        }
+    }
+}
+
+// Shading + reduction of the queued warp-frames: 32 consecutive queue slots = the 32 lanes of the K1 warp that pushed them.
+template <bool FUSED, bool FAST>
+__global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const EyeParams ep)
+{
+    const unsigned n = min(ep.queueCounters[0], ep.queueCap & ~31u);
+    const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
+    const float invS = 1.0f / (float)(uint32_t)ep.S;
+    const int lane = (int)(threadIdx.x & 31u);
+    for (unsigned q = blockIdx.x * 128u + threadIdx.x; q < n; q += gridDim.x * 128u) {        // n % 32 == 0: warp-uniform
+        const int4 hw = __ldcs(ep.queueHits + q);
+        const float4 q1 = __ldcs(ep.queueRays + 2 * (size_t)q + 1);
+        Hit h;
+        h.prim = hw.x; h.t = __int_as_float(hw.y); h.u = __int_as_float(hw.z); h.v = __int_as_float(hw.w);
+        const V3 col = (h.prim >= 0) ? shadeHit<FAST>(sc, h) : shadeMiss<FAST>(sc.missShader, mk(q1.x, q1.y, q1.z));
+        float cx = col.x * invS, cy = col.y * invS, cz = col.z * invS;
+        const unsigned id = __float_as_uint(q1.w) & 0x7fffffffu;
+        const unsigned f = id / total, r = id - f * total;
+        if (FUSED) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                cx += __shfl_xor_sync(kFullMask, cx, d);
+                cy += __shfl_xor_sync(kFullMask, cy, d);
+                cz += __shfl_xor_sync(kFullMask, cz, d);
+            }
+            if (lane == 0) {
+                const unsigned o = r / (unsigned)ep.S;
+                const unsigned blocksPerRow = (unsigned)ep.S >> 5, blk = (r - o * (unsigned)ep.S) >> 5;
+                __stcs(ep.partials + ((size_t)f * (unsigned)ep.N + o) * blocksPerRow + blk, make_float4(cx, cy, cz, 0.0f));
+            }
+        } else {
+            float* dst = ep.samples + 3 * ((size_t)f * total + r);
+            __stcs(dst, cx); __stcs(dst + 1, cy); __stcs(dst + 2, cz);
+        }
     }
 }
 
@@ -1342,6 +1517,16 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
     } else {
         if (eye.fast) launchTraceT<false, true>(sc, eye, grid, stream);
         else launchTraceT<false, false>(sc, eye, grid, stream);
+    }
+    if (eye.queueRays != nullptr && !eye.dumpHits) {                 // the queued warp-frames: trace with dynamic fetch, then shade
+        k_traceQueue<<<gridBlocks, kTraceThreads, 0, stream>>>(sc, eye);
+        if (eye.fused) {
+            if (eye.fast) k_shadeQueue<true, true><<<gridBlocks, 128, 0, stream>>>(sc, eye);
+            else k_shadeQueue<true, false><<<gridBlocks, 128, 0, stream>>>(sc, eye);
+        } else {
+            if (eye.fast) k_shadeQueue<false, true><<<gridBlocks, 128, 0, stream>>>(sc, eye);
+            else k_shadeQueue<false, false><<<gridBlocks, 128, 0, stream>>>(sc, eye);
+        }
     }
     if (eye.fast) launchSumT<true>(eye, stream);
     else launchSumT<false>(eye, stream);

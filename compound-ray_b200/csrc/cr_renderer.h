@@ -41,6 +41,8 @@ struct CompoundState {                 // device side of one CompoundEye camera
     int4* dEntries = nullptr; size_t entryCap = 0;   // entry frontier [frames][N] (k_buildEntries)
     int* dLists = nullptr; size_t listCap = 0;       // candidate lists [frames][N][16] (k_buildEntries stage 2)
     size_t listsLast = 0;                            // records written by the last launch (0: lists not built)
+    bool entriesValid = false; bool entriesLists = false; uint64_t entriesEyeVersion = 0;   // what dEntries/dLists row 0 was built for:
+    DevicePose entriesPose{};                                                               // a single frame of this eye at this pose
     float4* dPartials = nullptr; size_t partialCap = 0;   // fused reduction: [frames][N][S/32] warp partials
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; int2* dDumpC = nullptr; size_t dumpCap = 0;
