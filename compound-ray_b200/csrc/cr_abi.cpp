@@ -371,6 +371,28 @@ size_t crDebugCopyLastRayCounts(int32_t* counts2)
     CR_GUARD_END(0)
 }
 void crDebugSetCandidateLists(int on) { renderer().candidateLists = on; }
+void crDebugSetWavefront(int on, int refillBelow, double queueFraction)
+{
+    renderer().wavefront = on;
+    if (refillBelow > 0) renderer().wavefrontRefill = refillBelow;
+    if (queueFraction >= 0.0) renderer().queueFraction = queueFraction;
+}
+void crDebugSetNodeLanes(int lanes) { renderer().nodeLanes = lanes; }
+void crDebugSetFrameProfile(int on) { renderer().profileFrame = on != 0; }
+void crDebugFrameBreakdown(float* out3)
+{
+    CR_GUARD_BEGIN
+    if (out3) renderer().debugFrameBreakdown(out3);
+    CR_GUARD_END()
+}
+void crDebugSetDynamicChunks(int on) { renderer().dynamicChunks = on != 0; }
+void crDebugSetZeroCopy(int on) { renderer().zeroCopyFrames = on != 0; }
+unsigned long long crDebugLastQueuedRays()
+{
+    CR_GUARD_BEGIN
+    return renderer().debugLastQueuedRays();
+    CR_GUARD_END(0)
+}
 size_t crDebugCopyCandidateLists(int32_t* out, size_t records)
 {
     CR_GUARD_BEGIN

@@ -81,12 +81,21 @@ struct EyeParams {
     const DevicePose* poses = nullptr;   // device array [nFrames]; nullptr: use `pose`
     uchar4* fastRow = nullptr;           // when set: K1b also writes make_color(summed[i]) for i < fastRowCount
     int fastRowCount = 0;
+    uchar4* fastRowHost = nullptr;       // when set: the same pixels also go straight to the mapped pinned host frame
     const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
     // wavefront queue of the warp-frames whose ommatidium has no candidate list (k_traceCompound -> k_traceQueue -> k_shadeQueue)
-    float4* queueRays = nullptr;         // 2 float4 per ray: (origin, tmin), (direction, id = frame*N*S + r | inCone << 31)
+    float4* queueRays = nullptr;         // 2 float4 per ray: (origin, tmin), (direction, frame*N + ommatidium | inCone << 31)
+    int* queueWarps = nullptr;           // per 32 queue slots (one pushed warp-frame): its block of 32 samples within the row
     int4* queueHits = nullptr;           // (prim, t bits, u bits, v bits) per queued ray
     unsigned* queueCounters = nullptr;   // [0] rays pushed by K1 (multiples of 32), [1] rays handed out by k_traceQueue
     unsigned queueCap = 0;               // rays the queue holds; a warp that finds it full walks inline
+    int entryMaxLevels = 256;            // k_buildEntries: levels the frontier may descend (each is one dependent node fetch)
+    int chunkUnits = 1;                  // units of 32 rays per work-counter fetch of the single-frame trace kernel
+    unsigned* workCounter = nullptr;     // [0] chunks of ray units handed out beyond every warp's first, [1] warps that have left the
+                                         // kernel (the last one zeroes both for the next launch); nullptr: static split
+    int queueRefillBelow = 24;           // k_traceQueue fetches new rays when fewer lanes than this are still walking
+    int nodeLanes = 16;                  // phase switch of the per-lane BVH walk: leave the node loop for the pending leaves when
+                                         // fewer lanes than this still want a node (1 = classic while-while)
     float4* partials = nullptr;          // fused reduction: [nFrames][N][S/32] per-warp sums of 32 samples (K1 -> k_sumPartials)
     const int* lists = nullptr;          // [nFrames][N][16] candidate lists (k_buildEntries stage 2): header = element count, -1 = none
     bool fused = false;                  // in-kernel reduction (needs S % 32 == 0) instead of the ordered per-sample buffer
@@ -124,7 +133,8 @@ void launchRngInit(uint4* rng, int N, int S, unsigned long long firstFrame, unsi
 void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t stream);
 void launchBuildEntries(const DeviceScene& sc, const EyeParams& eye, int4* entries, int* lists, cudaStream_t stream);
 int candidateListStride();    // ints per (frame, ommatidium) record of the candidate lists
-void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream);
+void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream,
+                         cudaEvent_t afterTrace = nullptr);   // afterTrace: recorded between the trace and the reduction kernels
 void launchProjectVector(int mode, bool fast, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchProjectRaw(bool fast, const float* samples, int N, int S, uchar4* frame, int W, int H, cudaStream_t stream);
 void launchBuildProjectionMap(int mode, const float4* omm, int N, uint32_t* map, int W, int H, cudaStream_t stream);

@@ -344,18 +344,27 @@ __device__ __forceinline__ bool triTest(const float4* __restrict__ tri, const V3
 #define CR_SMEM_STACK 10   // measured: 32 -> 16 -> 10 levels = 19.6 -> 20.1 Grays/s batched, 15.07 -> 15.2 -> 15.4 per-frame API:
 #endif                     // with the entry frontier the stack stays shallow, and 5 KB/CTA leaves the SM a 192 KB L1
 
+#ifndef CR_EXP_STATE
+#define CR_EXP_STATE 0
+#endif
+#ifndef CR_INLINE_PHASED
+#define CR_INLINE_PHASED 0   // the per-lane walk INSIDE the trace kernel: 0 = while-while (traceClosest), 1 = phase-switched
+#endif
 constexpr int kSmemStack = CR_SMEM_STACK;
 constexpr int kLocalStack = 96 - CR_SMEM_STACK;   // shared + local levels >= 96 > the deepest possible LBVH (63 + 28 levels) + 3 entries
 constexpr int kSentinel = (int)0x80000000;
+constexpr unsigned kFullMask = 0xffffffffu;
 
+// The stack pointer is a plain member and the overflow levels live in an array OUTSIDE the struct (round 2): with the array
+// inside, the whole struct -- sp included -- was kept in local memory, and push/pop were a quarter of the walk's
+// instructions (profiles/r02i_traceQueue_phased_ncu_summary.txt).
 struct Stack {
-    int* smem;          // &sStack[0][tid], stride = block size
-    int stride;
+    int* smem;          // &sStack[0][tid]; rows are kTraceThreads ints apart
+    int* local;         // kLocalStack ints of thread-local memory for the levels beyond kSmemStack
     int sp;
-    int local[kLocalStack];
     __device__ __forceinline__ void push(int v)
     {
-        if (sp < kSmemStack) smem[sp * stride] = v;
+        if (sp < kSmemStack) smem[sp * kTraceThreads] = v;
         else local[sp - kSmemStack] = v;
         sp++;
     }
@@ -363,7 +372,7 @@ struct Stack {
     {
         if (sp == 0) return kSentinel;
         sp--;
-        return (sp < kSmemStack) ? smem[sp * stride] : local[sp - kSmemStack];
+        return (sp < kSmemStack) ? smem[sp * kTraceThreads] : local[sp - kSmemStack];
     }
 };
 
@@ -399,8 +408,9 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
     const float4* __restrict__ nodes = nodesAll + (size_t)(sx | (sy << 1) | (sz << 2)) * variantStride;
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+    int deep[kLocalStack];
     Stack st;
-    st.smem = sStackLane; st.stride = stackStride; st.sp = 0;
+    st.smem = sStackLane; st.local = deep; st.sp = 0;
     // Entry refs (k_buildEntries) are packed from .x and sorted near to far; the default is the root.
     int cur = entry.x;
     if (entry.y != kSentinel) {
@@ -451,6 +461,101 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
 }
 
 // ------------------------------------------------------------------------------------------
+// Phase-switched traversal (round 2).  In the while-while walk above a lane that has reached a leaf waits until EVERY lane
+// of its warp has reached one: with the unequal walks of rays that graze the scene the node loop runs at mean/max of the
+// per-lane step counts -- 10.5 of 32 lanes (profiles/r02g_traceQueue_whilewhile_ncu_summary.txt).  Here the warp votes
+// before every node step and leaves the node loop as soon as fewer than `nodeLanes` lanes still want a node while
+// somebody holds a leaf; the leaf holders test their triangles and pop, and everybody re-enters the node loop together.
+// Each lane performs exactly the operations of the while-while walk in the same order (a lane holding a leaf does not
+// look ahead), only the interleaving between lanes changes: same hits, same node/triangle counts.
+// The node step is written branch-light: one predicated push, one predicated pop, selects for the rest -- the four-way
+// branch of the walk above spent a quarter of its instructions on stack code at 3 to 5 lanes.
+// Must be called by all 32 lanes of a warp.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nodeStep(const float4* __restrict__ nodes, const int cur, const RayBox& rb, const float tmin,
+                                        const float tbest, Stack& st)
+{
+    const float4* np = nodes + 4 * (size_t)cur;
+    float4 n0, n1, n2, n3;
+    ldgNode(np, n0, n1, n2, n3);
+    const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), tmin));
+    const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), tbest));
+    const float tn1 = fmax3(fmaf(n1.x, rb.nix, rb.nax), fmaf(n1.z, rb.niy, rb.nay), fmaxf(fmaf(n2.z, rb.niz, rb.naz), tmin));
+    const float tf1 = fmin3(fmaf(n1.y, rb.fix, rb.fax), fmaf(n1.w, rb.fiy, rb.fay), fminf(fmaf(n2.w, rb.fiz, rb.faz), tbest));
+    const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
+    const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+    const bool firstIs0 = h0 && (!h1 || tn0 <= tn1);      // near child first; ties -> child 0 (as traceClosest)
+    int next = r0, other = r1;
+    if (!firstIs0) { next = r1; other = r0; }
+    if (h0 && h1) st.push(other);
+    if (!(h0 || h1)) next = st.pop();
+    return next;
+}
+
+__device__ __forceinline__ void leafStep(const float4* __restrict__ tris, const int leafRef, const V3 o, const V3 d, const float tmin,
+                                         Hit& best, int& triCount)
+{
+    const int x = ~leafRef;
+    const int first = x >> 3, cnt = (x & 7) + 1;
+    for (int k = 0; k < cnt; k++) {
+        float t, u, v;
+        int prim;
+        triCount++;
+        if (triTest(tris + 3 * (size_t)(first + k), o, d, tmin, best.t, t, u, v, prim)) {
+            if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
+        }
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ Hit traceClosestPhased(const float4* __restrict__ nodesAll, size_t variantStride,
+                                                  const float4* __restrict__ tris, const Ray& ray, const float tmax, int* sStackLane,
+                                                  int stackStride, int* nodeCount, int* triCount, const int4 entry, const int nodeLanes)
+{
+    RayBox rb;
+    int sx, sy, sz;
+    setupAxis(ray.o.x, ray.d.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
+    setupAxis(ray.o.y, ray.d.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
+    setupAxis(ray.o.z, ray.d.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
+    const float4* __restrict__ nodes = nodesAll + (size_t)(sx | (sy << 1) | (sz << 2)) * variantStride;
+    Hit best;
+    best.t = tmax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+    int deep[kLocalStack];
+    Stack st;
+    st.smem = sStackLane; st.local = deep; st.sp = 0;
+    int cur = entry.x;
+    if (entry.y != kSentinel) {
+        if (entry.z != kSentinel) {
+            if (entry.w != kSentinel) st.push(entry.w);
+            st.push(entry.z);
+        }
+        st.push(entry.y);
+    }
+    int nc = 0, tc = 0;
+    for (;;) {
+        unsigned leaves;
+        for (;;) {                                                  // one vote per node step while enough lanes want one
+            const int nWant = __popc(__ballot_sync(kFullMask, cur >= 0));
+            if (nWant < nodeLanes) {
+                leaves = __ballot_sync(kFullMask, cur < 0 && cur != kSentinel);
+                if (nWant == 0 || leaves != 0u) break;
+            }
+            if (cur >= 0) {
+                cur = nodeStep(nodes, cur, rb, ray.tmin, best.t, st);
+                if (COUNT) nc++;
+            }
+        }
+        if (leaves == 0u) break;                                    // nobody wants a node, nobody holds a leaf
+        if (cur < 0 && cur != kSentinel) {
+            leafStep(tris, cur, ray.o, ray.d, ray.tmin, best, tc);
+            cur = st.pop();
+        }
+    }
+    if (COUNT) { *nodeCount = nc; *triCount = tc; }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
 // Closest hit through an ommatidium's CANDIDATE LIST (k_buildEntries, second stage).  The sample cone of most
 // ommatidia reaches only a handful of BVH leaves; for those the frontier pass flattens the part of the tree the
 // cone can reach into a short list of "pre-leaf" elements (node index, which of its two children are reachable
@@ -465,7 +570,6 @@ __device__ __forceinline__ Hit traceClosest(const float4* __restrict__ nodesAll,
 // closest hit so far) -- and with the lowest-primitive tie rule the closest hit, hence every output bit, is the same.
 // Must be called by all 32 lanes of the warp; `list` is warp-uniform.
 // ------------------------------------------------------------------------------------------
-constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kListMax = 15;                 // elements per (frame, ommatidium); the record is 1 + kListMax ints = 64 B
 constexpr int kListStride = kListMax + 1;
 constexpr int kListFallback = -1;            // header value: no list -- walk the entry frontier per lane
@@ -600,6 +704,9 @@ __device__ __forceinline__ uchar4 makeColorMode(bool fast, float r, float g, flo
 #ifndef CR_ENTRY_BUDGET
 #define CR_ENTRY_BUDGET 4
 #endif
+#ifndef CR_ENTRY_PREFETCH
+#define CR_ENTRY_PREFETCH 0   // measured: 46 us instead of 36 us per headline frame with the prefetch (the extra L1 fills cost more than they hide)
+#endif
 constexpr int kEntryK = 4;                      // slots of the int4 record
 constexpr int kEntryBudget = CR_ENTRY_BUDGET;   // entries actually handed out (<= kEntryK)
 
@@ -621,6 +728,17 @@ __device__ __forceinline__ bool coneMayTouchBox(const ConePyramid& P, const V3 b
     const float M = fmaxf(P.axis.x * lo.x, P.axis.x * hi.x) + fmaxf(P.axis.y * lo.y, P.axis.y * hi.y) + fmaxf(P.axis.z * lo.z, P.axis.z * hi.z);
     if (M < -tol) return false;                         // wholly behind the apex
     return true;
+}
+
+// Child boxes of a node read from the copy of direction octant (sx, sy, sz): that copy stores (near, far) per axis, i.e.
+// (max, min) on the axes whose sign bit is set (cr_bvh.cu k_emitNodes) -- swap them back.
+__device__ __forceinline__ void nodeBoxes(const float4 n0, const float4 n1, const float4 n2, const bool sx, const bool sy, const bool sz,
+                                          V3& min0, V3& max0, V3& min1, V3& max1)
+{
+    min0 = mk(sx ? n0.y : n0.x, sy ? n0.w : n0.z, sz ? n2.y : n2.x);
+    max0 = mk(sx ? n0.x : n0.y, sy ? n0.z : n0.w, sz ? n2.x : n2.y);
+    min1 = mk(sx ? n1.y : n1.x, sy ? n1.w : n1.z, sz ? n2.w : n2.z);
+    max1 = mk(sx ? n1.x : n1.y, sy ? n1.z : n1.w, sz ? n2.z : n2.w);
 }
 
 // kEntryK lanes work on one (frame, ommatidium): lane j owns slot j of the frontier, fetches that
@@ -678,13 +796,20 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     C.n2 = vadd(vmuls(v, ch), back);
     C.n3 = vadd(vmuls(v, -ch), back);
 
+    // The pass reads the node copy of the CONE AXIS's direction octant -- the copy most of this ommatidium's sample rays will
+    // read in the trace kernel -- and swaps its (near, far) planes back to (min, max): what it fetches is then warm in L2 for
+    // the rays (and, while the camera moves slowly, already warm from the previous frame's rays), instead of living in copy 0
+    // that no ray of this cone touches.
+    const bool csx = C.axis.x < 0.0f, csy = C.axis.y < 0.0f, csz = C.axis.z < 0.0f;
+    const float4* __restrict__ coneNodes = sc.nodes + (size_t)((csx ? 1 : 0) | (csy ? 2 : 0) | (csz ? 4 : 0)) * sc.nodeVariantStride;
+
     EntryList L;
 #pragma unroll
     for (int k = 0; k < kEntryK; k++) { L.ref[k] = kSentinel; L.key[k] = 0.0f; }
     L.ref[0] = 0;
     L.n = 1;
     L.fin = ok ? 0u : 1u;                       // not ok: the root stays the only entry
-    for (int iter = 0; iter < 256; iter++) {
+    for (int iter = 0; iter < ep.entryMaxLevels; iter++) {      // (stopping early leaves a coarser but equally valid frontier)
         int myRef = kSentinel;
 #pragma unroll
         for (int k = 0; k < kEntryK; k++) if (k == lane) myRef = L.ref[k];
@@ -693,12 +818,18 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
         int r0 = kSentinel, r1 = kSentinel, flags = 0;
         float k0 = 0.0f, k1 = 0.0f;
         if (active) {
-            const float4* np = sc.nodes + 4 * (size_t)myRef;        // octant variant 0 = (min, max)
+            const float4* np = coneNodes + 4 * (size_t)myRef;
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            const V3 min0 = mk(n0.x, n0.z, n2.x), max0 = mk(n0.y, n0.w, n2.y);
-            const V3 min1 = mk(n1.x, n1.z, n2.z), max1 = mk(n1.y, n1.w, n2.w);
-            const bool h0 = coneMayTouchBox(C, min0, max0), h1 = coneMayTouchBox(C, min1, max1);
+            V3 min0, max0, min1, max1;
+            nodeBoxes(n0, n1, n2, csx, csy, csz, min0, max0, min1, max1);
             r0 = __float_as_int(n3.x); r1 = __float_as_int(n3.y);
+#if CR_ENTRY_PREFETCH
+            // The descent is a chain of dependent node fetches: start pulling both children into L1 now, so that the cone
+            // tests below overlap the next level's memory latency instead of preceding it.
+            if (r0 >= 0) { const float4* c = sc.nodes + 4 * (size_t)r0; asm volatile("prefetch.global.L1 [%0];" ::"l"(c)); asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 2)); }
+            if (r1 >= 0) { const float4* c = sc.nodes + 4 * (size_t)r1; asm volatile("prefetch.global.L1 [%0];" ::"l"(c)); asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 2)); }
+#endif
+            const bool h0 = coneMayTouchBox(C, min0, max0), h1 = coneMayTouchBox(C, min1, max1);
             k0 = vdot(C.axis, vsub(vmuls(vadd(min0, max0), 0.5f), C.apex));
             k1 = vdot(C.axis, vsub(vmuls(vadd(min1, max1), 0.5f), C.apex));
             // never hand out leaves: their triangles would be tested without the per-ray box test
@@ -760,10 +891,10 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     while (sp > 0 && good) {
         const int node = stack[--sp];
         if (++visits > kListVisits) { good = false; break; }
-        const float4* np = sc.nodes + 4 * (size_t)node;             // octant variant 0 = (min, max)
+        const float4* np = coneNodes + 4 * (size_t)node;
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-        const V3 min0 = mk(n0.x, n0.z, n2.x), max0 = mk(n0.y, n0.w, n2.y);
-        const V3 min1 = mk(n1.x, n1.z, n2.z), max1 = mk(n1.y, n1.w, n2.w);
+        V3 min0, max0, min1, max1;
+        nodeBoxes(n0, n1, n2, csx, csy, csz, min0, max0, min1, max1);
         const bool h0 = coneMayTouchBox(C, min0, max0), h1 = coneMayTouchBox(C, min1, max1);
         const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
         const int mask = ((h0 && r0 < 0) ? 1 : 0) | ((h1 && r1 < 0) ? 2 : 0);
@@ -831,13 +962,50 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     int* sWarp = &sStack[0][threadIdx.x & ~31u];
     // S % 32 == 0: the 32 rays of a warp are samples of ONE ommatidium (and `r < total` is warp-uniform)
     const bool warpRows = (ep.S & 31) == 0;
-    for (unsigned r = blockIdx.x * kTraceThreads + threadIdx.x; r < total; r += stride) {
-        if (r + stride < total) {                       // warm L2 with the next ray's RNG state
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * (size_t)(r + stride)));
+    // Work distribution (round 2): a warp's unit is 32 consecutive rays (x F frames in a batch); units are handed out in
+    // CHUNKS of ep.chunkUnits (1 in a batch) -- the first chunk of every warp by its position in the grid, the following
+    // ones from a global counter (one atomic per chunk, issued a whole chunk before its answer is needed).  With the static grid-stride split the warps finished up to 15 % apart (sky, listed, walking and queued units
+    // cost between 1x and 6x; sm__warps_active 41.8 of 50 %, profiles/r02j_k1_queue_ncu_summary.txt).
+    const unsigned gridWarps = gridDim.x * (kTraceThreads / 32u);
+    const unsigned nUnits = (total + 31u) >> 5;
+    const unsigned chunkUnits = MULTI ? 1u : (unsigned)max(1, ep.chunkUnits);
+    const unsigned nChunks = (nUnits + chunkUnits - 1u) / chunkUnits;
+    // Two chunks are known ahead (the first two of every warp by its position in the grid): while chunk i is traced, the
+    // RNG state of chunk i+1 is already on its way to L2 and the counter is asked for chunk i+2.
+    unsigned chunk = blockIdx.x * (kTraceThreads / 32u) + (threadIdx.x >> 5);
+    unsigned nextChunk = chunk + gridWarps;
+    while (chunk < nChunks) {                                              // (warp-uniform)
+      unsigned afterNext = nextChunk + gridWarps;                           // static split when there is no counter
+      if (ep.workCounter != nullptr && lane == 0) afterNext = atomicAdd(ep.workCounter, 1u) + 2u * gridWarps;
+      {
+          const size_t rn = ((size_t)nextChunk * chunkUnits << 5) + (unsigned)lane;
+          if (rn < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * rn));
+      }
+      for (unsigned k = 0; k < chunkUnits; k++) {
+        const unsigned unit = chunk * chunkUnits + k;
+        if (unit >= nUnits) break;                                          // (warp-uniform)
+        const unsigned r0 = (unit << 5) + (unsigned)lane;
+#if CR_INLINE_PHASED
+        // a warp stays whole (the phased traversal votes across its lanes): the lanes of the last warp beyond the last
+        // ray (N*S % 32 != 0) redo ray total-1 and store nothing
+        const bool valid = r0 < total;
+        const unsigned r = valid ? r0 : total - 1u;
+#else
+        constexpr bool valid = true;
+        const unsigned r = r0;
+        if (r0 < total) {
+#endif
+        if (k + 1u < chunkUnits && r0 + 32u < total) {                      // warm L2 with the next unit's RNG state
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * (size_t)(r0 + 32u)));
         }
         const unsigned o = r / (unsigned)ep.S;
         uint4* statePtr = ep.rng + 2 * (size_t)r;
+#if CR_EXP_STATE >= 2      // timing experiment only (wrong streams): no state load
+        Rng rng;
+        rng.d = r; rng.v0 = r * 2654435761u; rng.v1 = r ^ 0x9e3779b9u; rng.v2 = r + 77u; rng.v3 = ~r; rng.v4 = r * 40503u + 1u; rng.flag = 0; rng.extra = 0.0f;
+#else
         Rng rng = rngLoad(statePtr);
+#endif
         // Consecutive frames of one sample stream are processed back to back by the same lane: the
         // state is loaded and stored once per batch, and one launch covers F frames (poses).
         for (int f = 0; f < F; f++) {
@@ -857,8 +1025,10 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
             if (MULTI) {   // park the state in shared memory: its 8 registers are dead while the ray is traced
                 sRng[0][threadIdx.x] = make_uint4(rng.d, rng.v0, rng.v1, rng.v2);
                 sRng[1][threadIdx.x] = make_uint4(rng.v3, rng.v4, (uint32_t)rng.flag, __float_as_uint(rng.extra));
-            } else {
+            } else if (valid) {
+#if CR_EXP_STATE < 1       // timing experiment only: no state store
                 rngStore(statePtr, rng);
+#endif
             }
             int nNode = 0, nTri = 0;
             Hit h;
@@ -883,18 +1053,26 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                     if (lane == 0) base = atomicAdd(ep.queueCounters, 32u);
                     base = __shfl_sync(kFullMask, base, 0);
                     if (base + 32u <= ep.queueCap) {
+                        // record: origin, tmin | direction, (frame*N + ommatidium) with the in-cone flag on top; the warp's
+                        // position in its row (block of 32 samples) goes to the per-warp header for k_shadeQueue
                         const unsigned slot = base + (unsigned)lane;
-                        const unsigned id = ((unsigned)f * total + r) | (inCone ? 0x80000000u : 0u);
+                        const unsigned id = ((unsigned)f * (unsigned)ep.N + o) | (inCone ? 0x80000000u : 0u);
                         __stcs(ep.queueRays + 2 * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, ray.tmin));
                         __stcs(ep.queueRays + 2 * (size_t)slot + 1, make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(id)));
+                        if (lane == 0) ep.queueWarps[base >> 5] = (int)((r - o * (unsigned)ep.S) >> 5);
                         queued = true;
                     }
                 }
                 if (!queued) {
                     int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
                     if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+#if CR_INLINE_PHASED
+                    h = traceClosestPhased<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
+                                                 &nNode, &nTri, entry, ep.nodeLanes);
+#else
                     h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
                                            &nNode, &nTri, entry);
+#endif
                 }
             }
             if (queued) {                                   // (warp-uniform) shaded and reduced by k_shadeQueue
@@ -919,7 +1097,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                     const unsigned blk = (r - o * (unsigned)ep.S) >> 5;
                     __stcs(ep.partials + ((size_t)f * (unsigned)ep.N + o) * blocksPerRow + blk, make_float4(cx, cy, cz, 0.0f));
                 }
-            } else {
+            } else if (valid) {
                 float* dst = ep.samples + 3 * ((size_t)f * total + r);
                 __stcs(dst, cx); __stcs(dst + 1, cy); __stcs(dst + 2, cz);
             }
@@ -928,7 +1106,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 rng.d = a.x; rng.v0 = a.y; rng.v1 = a.z; rng.v2 = a.w; rng.v3 = b.x; rng.v4 = b.y;
                 rng.flag = (int)b.z; rng.extra = __uint_as_float(b.w);
             }
-            if (DUMP) {
+            if (DUMP && valid) {
                 const unsigned s = r - o * (unsigned)ep.S;
                 const size_t id = (size_t)ep.N * s + o;                                 // reference stream-id order
                 ep.dumpOrigins[3 * id] = ray.o.x; ep.dumpOrigins[3 * id + 1] = ray.o.y; ep.dumpOrigins[3 * id + 2] = ray.o.z;
@@ -937,31 +1115,38 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 if (ep.dumpCounts) ep.dumpCounts[id] = make_int2(nNode, nTri);   // nodes fetched / triangles tested by THIS kernel
             }
         }
-        if (MULTI) rngStore(statePtr, rng);
+        if (MULTI && valid) rngStore(statePtr, rng);
+#if !CR_INLINE_PHASED
+        }
+#endif
+      }
+      chunk = nextChunk;
+      nextChunk = __shfl_sync(kFullMask, afterNext, 0);
+    }
+    // The last warp of the grid to leave rearms the counters for the next launch (no memset between frames).
+    if (ep.workCounter != nullptr && lane == 0) {
+        if (atomicAdd(ep.workCounter + 1, 1u) == gridWarps - 1u) { atomicExch(ep.workCounter, 0u); atomicExch(ep.workCounter + 1, 0u); }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // Wavefront queue (batches).  K1 pushes the warp-frames it would have walked per lane; k_traceQueue traces them with
-// DYNAMIC RAY FETCH: persistent warps whose lanes pull the next ray of the queue as soon as their own is finished (checked
-// after every leaf round, refilled when fewer than kRefillBelow lanes are busy), so the node loop stays populated however
-// unequal the walks are -- the grazing ommatidia this path exists for visit 5 to 60 nodes per ray.  The closest hit does
+// DYNAMIC RAY FETCH (persistent warps whose lanes pull the next ray of the queue when fewer than ep.queueRefillBelow lanes
+// are still busy) and PHASE SWITCHING (the node loop is left as soon as fewer than ep.nodeLanes lanes want a node while
+// somebody holds a leaf), so the node loop stays populated however unequal the walks are -- the grazing ommatidia this
+// path exists for visit 5 to 60 nodes per ray.  The closest hit does
 // not depend on which lane or kernel finds it (same box test, same triangle test, lowest-primitive tie rule), and
 // k_shadeQueue turns hits into colours and sums them warp-frame by warp-frame in K1's lane order: same output bits.
 // ------------------------------------------------------------------------------------------
-#ifndef CR_REFILL_BELOW
-#define CR_REFILL_BELOW 24
-#endif
-constexpr int kRefillBelow = CR_REFILL_BELOW;
-
 __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceQueue(const DeviceScene sc, const EyeParams ep)
 {
     __shared__ int sStack[kSmemStack][kTraceThreads];
     const unsigned n = min(ep.queueCounters[0], ep.queueCap & ~31u);
     const int lane = (int)(threadIdx.x & 31u);
-    const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
+    const int nodeLanes = ep.nodeLanes, refillBelow = ep.queueRefillBelow;
+    int deep[kLocalStack];
     Stack st;
-    st.smem = &sStack[0][threadIdx.x]; st.stride = kTraceThreads; st.sp = 0;
+    st.smem = &sStack[0][threadIdx.x]; st.local = deep; st.sp = 0;
     RayBox rb;
     rb.nix = rb.niy = rb.niz = rb.fix = rb.fiy = rb.fiz = rb.nax = rb.nay = rb.naz = rb.fax = rb.fay = rb.faz = 0.0f;
     V3 ro = mk(0.0f, 0.0f, 0.0f), rd = mk(0.0f, 0.0f, 1.0f);
@@ -972,84 +1157,63 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceQue
     int cur = kSentinel;
     unsigned slot = 0u;
     bool active = false, exhausted = false;
+    int tc = 0;
     for (;;) {
-        if (!exhausted) {                                             // ---- refill the idle lanes
-            const unsigned need = __ballot_sync(kFullMask, !active);
-            if (need != 0u) {
-                const int leader = __ffs((int)need) - 1;
-                unsigned base = 0u;
-                if (lane == leader) base = atomicAdd(ep.queueCounters + 1, (unsigned)__popc(need));
-                base = __shfl_sync(kFullMask, base, leader);
-                if (base + (unsigned)__popc(need) >= n) exhausted = true;
-                const unsigned my = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                if (!active && my < n) {
-                    const float4 q0 = __ldcs(ep.queueRays + 2 * (size_t)my), q1 = __ldcs(ep.queueRays + 2 * (size_t)my + 1);
-                    ro = mk(q0.x, q0.y, q0.z); tmin = q0.w; rd = mk(q1.x, q1.y, q1.z);
-                    const unsigned idw = __float_as_uint(q1.w);
-                    int sx, sy, sz;
-                    setupAxis(ro.x, rd.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
-                    setupAxis(ro.y, rd.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
-                    setupAxis(ro.z, rd.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
-                    nodes = sc.nodes + (size_t)(sx | (sy << 1) | (sz << 2)) * sc.nodeVariantStride;
-                    best.t = kTMax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
-                    st.sp = 0;
-                    int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
-                    if (ep.entries != nullptr && (idw & 0x80000000u)) {
-                        const unsigned id = idw & 0x7fffffffu;
-                        const unsigned f = id / total, o = (id - f * total) / (unsigned)ep.S;
-                        entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
-                    }
-                    cur = entry.x;
-                    if (entry.y != kSentinel) {
-                        if (entry.z != kSentinel) {
-                            if (entry.w != kSentinel) st.push(entry.w);
-                            st.push(entry.z);
-                        }
-                        st.push(entry.y);
-                    }
-                    slot = my;
-                    active = true;
-                }
-            }
+        // ---- retire the finished rays, hand new ones to the idle lanes
+        if (active && cur == kSentinel) {
+            __stcs(ep.queueHits + slot, make_int4(best.prim, __float_as_int(best.t), __float_as_int(best.u), __float_as_int(best.v)));
+            active = false;
         }
-        if (__ballot_sync(kFullMask, active) == 0u) break;
-        for (;;) {                                                    // ---- walk; leave to refill when the warp thins out
-            while (cur >= 0) {
-                const float4* np = nodes + 4 * (size_t)cur;
-                float4 n0, n1, n2, n3;
-                ldgNode(np, n0, n1, n2, n3);
-                const float tn0 = fmax3(fmaf(n0.x, rb.nix, rb.nax), fmaf(n0.z, rb.niy, rb.nay), fmaxf(fmaf(n2.x, rb.niz, rb.naz), tmin));
-                const float tf0 = fmin3(fmaf(n0.y, rb.fix, rb.fax), fmaf(n0.w, rb.fiy, rb.fay), fminf(fmaf(n2.y, rb.fiz, rb.faz), best.t));
-                const float tn1 = fmax3(fmaf(n1.x, rb.nix, rb.nax), fmaf(n1.z, rb.niy, rb.nay), fmaxf(fmaf(n2.z, rb.niz, rb.naz), tmin));
-                const float tf1 = fmin3(fmaf(n1.y, rb.fix, rb.fax), fmaf(n1.w, rb.fiy, rb.fay), fminf(fmaf(n2.w, rb.fiz, rb.faz), best.t));
-                const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
-                const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    const bool firstIs0 = tn0 <= tn1;
-                    cur = firstIs0 ? r0 : r1;
-                    st.push(firstIs0 ? r1 : r0);
-                } else if (h0) cur = r0;
-                else if (h1) cur = r1;
-                else cur = st.pop();
-            }
-            if (cur != kSentinel) {
-                const int x = ~cur;
-                const int first = x >> 3, cnt = (x & 7) + 1;
-                for (int k = 0; k < cnt; k++) {
-                    float t, u, v;
-                    int prim;
-                    if (triTest(sc.tris + 3 * (size_t)(first + k), ro, rd, tmin, best.t, t, u, v, prim)) {
-                        if (t < best.t || best.prim < 0 || prim < best.prim) { best.t = t; best.prim = prim; best.u = u; best.v = v; }
+        unsigned live = __ballot_sync(kFullMask, active);
+        if (!exhausted && __popc(live) < refillBelow) {
+            const unsigned need = ~live;
+            const int leader = __ffs((int)need) - 1;
+            unsigned base = 0u;
+            if (lane == leader) base = atomicAdd(ep.queueCounters + 1, (unsigned)__popc(need));
+            base = __shfl_sync(kFullMask, base, leader);
+            if (base + (unsigned)__popc(need) >= n) exhausted = true;
+            const unsigned my = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+            if (!active && my < n) {
+                const float4 q0 = __ldcs(ep.queueRays + 2 * (size_t)my), q1 = __ldcs(ep.queueRays + 2 * (size_t)my + 1);
+                ro = mk(q0.x, q0.y, q0.z); tmin = q0.w; rd = mk(q1.x, q1.y, q1.z);
+                const unsigned idw = __float_as_uint(q1.w);
+                int sx, sy, sz;
+                setupAxis(ro.x, rd.x, rb.nix, rb.fix, rb.nax, rb.fax, sx);
+                setupAxis(ro.y, rd.y, rb.niy, rb.fiy, rb.nay, rb.fay, sy);
+                setupAxis(ro.z, rd.z, rb.niz, rb.fiz, rb.naz, rb.faz, sz);
+                nodes = sc.nodes + (size_t)(sx | (sy << 1) | (sz << 2)) * sc.nodeVariantStride;
+                best.t = kTMax; best.prim = -1; best.u = 0.0f; best.v = 0.0f;
+                st.sp = 0;
+                int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
+                if (ep.entries != nullptr && (idw & 0x80000000u)) entry = __ldg(ep.entries + (idw & 0x7fffffffu));
+                cur = entry.x;
+                if (entry.y != kSentinel) {
+                    if (entry.z != kSentinel) {
+                        if (entry.w != kSentinel) st.push(entry.w);
+                        st.push(entry.z);
                     }
+                    st.push(entry.y);
                 }
-                cur = st.pop();
+                slot = my;
+                active = true;
             }
-            if (active && cur == kSentinel) {
-                __stcs(ep.queueHits + slot, make_int4(best.prim, __float_as_int(best.t), __float_as_int(best.u), __float_as_int(best.v)));
-                active = false;
+            live = __ballot_sync(kFullMask, active);
+        }
+        if (live == 0u) break;
+        // ---- leaf phase: the lanes that hold a leaf test its triangles and pop
+        if (cur < 0 && cur != kSentinel) {
+            leafStep(sc.tris, cur, ro, rd, tmin, best, tc);
+            cur = st.pop();
+        }
+        // ---- node phase: one vote per step; below the threshold the warp leaves as soon as somebody holds a leaf or has
+        //      finished and can be replaced (a second vote, taken only then)
+        for (;;) {
+            const int nWant = __popc(__ballot_sync(kFullMask, cur >= 0));
+            if (nWant < nodeLanes) {
+                if (nWant == 0) break;
+                if (__any_sync(kFullMask, cur < 0 && (cur != kSentinel || (active && !exhausted)))) break;
             }
-            const unsigned live = __ballot_sync(kFullMask, active);
-            if (live == 0u || (!exhausted && __popc(live) < kRefillBelow)) break;
+            if (cur >= 0) cur = nodeStep(nodes, cur, rb, tmin, best.t, st);
         }
     }
 }
@@ -1059,7 +1223,6 @@ template <bool FUSED, bool FAST>
 __global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const EyeParams ep)
 {
     const unsigned n = min(ep.queueCounters[0], ep.queueCap & ~31u);
-    const unsigned total = (unsigned)ep.N * (unsigned)ep.S;
     const float invS = 1.0f / (float)(uint32_t)ep.S;
     const int lane = (int)(threadIdx.x & 31u);
     for (unsigned q = blockIdx.x * 128u + threadIdx.x; q < n; q += gridDim.x * 128u) {        // n % 32 == 0: warp-uniform
@@ -1069,8 +1232,8 @@ __global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const 
         h.prim = hw.x; h.t = __int_as_float(hw.y); h.u = __int_as_float(hw.z); h.v = __int_as_float(hw.w);
         const V3 col = (h.prim >= 0) ? shadeHit<FAST>(sc, h) : shadeMiss<FAST>(sc.missShader, mk(q1.x, q1.y, q1.z));
         float cx = col.x * invS, cy = col.y * invS, cz = col.z * invS;
-        const unsigned id = __float_as_uint(q1.w) & 0x7fffffffu;
-        const unsigned f = id / total, r = id - f * total;
+        const size_t row = __float_as_uint(q1.w) & 0x7fffffffu;                                // frame*N + ommatidium
+        const unsigned blk = (unsigned)__ldg(ep.queueWarps + (q >> 5));                         // block of 32 samples within the row
         if (FUSED) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -1078,13 +1241,9 @@ __global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const 
                 cy += __shfl_xor_sync(kFullMask, cy, d);
                 cz += __shfl_xor_sync(kFullMask, cz, d);
             }
-            if (lane == 0) {
-                const unsigned o = r / (unsigned)ep.S;
-                const unsigned blocksPerRow = (unsigned)ep.S >> 5, blk = (r - o * (unsigned)ep.S) >> 5;
-                __stcs(ep.partials + ((size_t)f * (unsigned)ep.N + o) * blocksPerRow + blk, make_float4(cx, cy, cz, 0.0f));
-            }
+            if (lane == 0) __stcs(ep.partials + row * ((unsigned)ep.S >> 5) + blk, make_float4(cx, cy, cz, 0.0f));
         } else {
-            float* dst = ep.samples + 3 * ((size_t)f * total + r);
+            float* dst = ep.samples + 3 * (row * (unsigned)ep.S + 32u * blk + (unsigned)lane);
             __stcs(dst, cx); __stcs(dst + 1, cy); __stcs(dst + 2, cz);
         }
     }
@@ -1093,28 +1252,42 @@ __global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const 
 // K1b of the fused mode: summed[f][o] = fixed-order sum of the S/32 warp partials of the row, one warp per row.
 // Lane l first adds partials l, l+32, l+64, ... in ascending order, then the same butterfly as in K1 combines the 32
 // lanes (S <= 1024: one partial per lane).  Also writes the 8-bit row of single_dimension_fast / pose batches.
+constexpr int kSumPartialRows = 32;          // rows (warps) per CTA of k_sumPartials: its 32 pixels leave as ONE 128-byte store
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_sumPartials(const float4* __restrict__ partials, int NF, int blocksPerRow, float4* __restrict__ summed,
-                                                     uchar4* __restrict__ fastRow, int fastRowCount)
+__global__ void __launch_bounds__(32 * kSumPartialRows) k_sumPartials(const float4* __restrict__ partials, int NF, int blocksPerRow,
+                                                                      float4* __restrict__ summed, uchar4* __restrict__ fastRow,
+                                                                      int fastRowCount, uchar4* __restrict__ fastRowHost)
 {
-    const int row = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
-    const int lane = (int)(threadIdx.x & 31u);
-    if (row >= NF) return;                                   // warp-uniform
-    const float4* p = partials + (size_t)row * blocksPerRow;
-    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-    for (int k = lane; k < blocksPerRow; k += 32) {
-        const float4 q = __ldcs(p + k);
-        cx += q.x; cy += q.y; cz += q.z;
-    }
+    __shared__ uchar4 sPx[kSumPartialRows];
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    const int row0 = (int)blockIdx.x * kSumPartialRows, row = row0 + warp;
+    if (row < NF) {                                          // warp-uniform
+        const float4* p = partials + (size_t)row * blocksPerRow;
+        float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+        for (int k = lane; k < blocksPerRow; k += 32) {
+            const float4 q = __ldcs(p + k);
+            cx += q.x; cy += q.y; cz += q.z;
+        }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        cx += __shfl_xor_sync(kFullMask, cx, d);
-        cy += __shfl_xor_sync(kFullMask, cy, d);
-        cz += __shfl_xor_sync(kFullMask, cz, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            cx += __shfl_xor_sync(kFullMask, cx, d);
+            cy += __shfl_xor_sync(kFullMask, cy, d);
+            cz += __shfl_xor_sync(kFullMask, cz, d);
+        }
+        if (lane == 0) {
+            summed[row] = make_float4(cx, cy, cz, 0.0f);
+            if (fastRow != nullptr) sPx[warp] = makeColor<FAST>(cx, cy, cz);
+        }
     }
-    if (lane == 0) {
-        summed[row] = make_float4(cx, cy, cz, 0.0f);
-        if (fastRow != nullptr && row < fastRowCount) fastRow[row] = makeColor<FAST>(cx, cy, cz);
+    if (fastRow == nullptr) return;                          // (uniform)
+    __syncthreads();
+    // the CTA's 32 pixels as one coalesced 128-byte store -- to the device frame and, when the caller reads every frame,
+    // straight into the pinned (mapped) host frame: 313 PCIe writes of 128 bytes per 10 000-ommatidia row instead of a
+    // copy queued behind the kernel (or 10 000 writes of 4 bytes: 22 us)
+    if (warp == 0 && row0 + lane < NF && row0 + lane < fastRowCount) {
+        const uchar4 px = sPx[lane];
+        fastRow[row0 + lane] = px;
+        if (fastRowHost != nullptr) fastRowHost[row0 + lane] = px;
     }
 }
 
@@ -1136,7 +1309,7 @@ __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc)
 
 template <bool FAST>
 __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
-                                                            uchar4* __restrict__ fastRow, int fastRowCount)
+                                                            uchar4* __restrict__ fastRow, int fastRowCount, uchar4* __restrict__ fastRowHost)
 {
     __shared__ float tile[kSumStages][kSumRows * kSumStride];
     const int row0 = blockIdx.x * kSumRows;
@@ -1182,7 +1355,11 @@ __global__ void __launch_bounds__(kSumThreads) k_sumSamples(const float* __restr
     // written here instead of by a separate projection launch.  Warp 0 holds (row, channel) at lane 3*row+ch.
     if (fastRow != nullptr && t < 32) {
         const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
-        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor<FAST>(sum, g, b);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) {
+            const uchar4 px = makeColor<FAST>(sum, g, b);
+            fastRow[row0 + myRow] = px;
+            if (fastRowHost != nullptr) fastRowHost[row0 + myRow] = px;
+        }
     }
 }
 
@@ -1216,7 +1393,7 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
 
 template <bool FAST>
 __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ samples, int NF, int S, float4* __restrict__ summed,
-                                                      uchar4* __restrict__ fastRow, int fastRowCount)
+                                                      uchar4* __restrict__ fastRow, int fastRowCount, uchar4* __restrict__ fastRowHost)
 {
     __shared__ __align__(128) float tile[kSumStages][kSumRows * kTmaStride];
     __shared__ __align__(8) uint64_t full[kSumStages];
@@ -1265,7 +1442,11 @@ __global__ void __launch_bounds__(32) k_sumSamplesTma(const float* __restrict__ 
     if (summing) reinterpret_cast<float*>(summed + row0 + myRow)[ch] = sum;
     if (fastRow != nullptr) {
         const float g = __shfl_down_sync(0xffffffffu, sum, 1), b = __shfl_down_sync(0xffffffffu, sum, 2);
-        if (summing && ch == 0 && row0 + myRow < fastRowCount) fastRow[row0 + myRow] = makeColor<FAST>(sum, g, b);
+        if (summing && ch == 0 && row0 + myRow < fastRowCount) {
+            const uchar4 px = makeColor<FAST>(sum, g, b);
+            fastRow[row0 + myRow] = px;
+            if (fastRowHost != nullptr) fastRowHost[row0 + myRow] = px;
+        }
     }
 }
 
@@ -1488,21 +1669,21 @@ static void launchSumT(const EyeParams& eye, cudaStream_t stream)
 {
     const long long nf = (long long)eye.N * eye.nFrames;
     if (eye.fused) {
-        k_sumPartials<FAST><<<(unsigned)((nf * 32 + 127) / 128), 128, 0, stream>>>(eye.partials, (int)nf, eye.S >> 5, eye.summed, eye.fastRow,
-                                                                                  eye.fastRowCount);
+        k_sumPartials<FAST><<<(unsigned)((nf + kSumPartialRows - 1) / kSumPartialRows), 32 * kSumPartialRows, 0, stream>>>(eye.partials, (int)nf, eye.S >> 5, eye.summed, eye.fastRow,
+                                                                                  eye.fastRowCount, eye.fastRowHost);
         return;
     }
     static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();
     const unsigned sumGrid = (unsigned)((nf + kSumRows - 1) / kSumRows);
     if (useTma && eye.S % 4 == 0)
-        k_sumSamplesTma<FAST><<<sumGrid, 32, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+        k_sumSamplesTma<FAST><<<sumGrid, 32, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount, eye.fastRowHost);
     else
-        k_sumSamples<FAST><<<sumGrid, kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount);
+        k_sumSamples<FAST><<<sumGrid, kSumThreads, 0, stream>>>(eye.samples, (int)nf, eye.S, eye.summed, eye.fastRow, eye.fastRowCount, eye.fastRowHost);
 }
 
 // K1 + K1b.  eye.fused (needs S % 32 == 0 and eye.partials) selects the in-kernel reduction, eye.fast the hardware
 // elementary functions; the per-ray dump exists for the ordered single-frame kernel only.
-void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream)
+void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBlocks, cudaStream_t stream, cudaEvent_t afterTrace)
 {
     const long long total = (long long)eye.N * eye.S;
     if (total <= 0) return;
@@ -1528,6 +1709,7 @@ void launchTraceCompound(const DeviceScene& sc, const EyeParams& eye, int gridBl
             else k_shadeQueue<false, false><<<gridBlocks, 128, 0, stream>>>(sc, eye);
         }
     }
+    if (afterTrace != nullptr) cudaEventRecord(afterTrace, stream);
     if (eye.fast) launchSumT<true>(eye, stream);
     else launchSumT<false>(eye, stream);
 }

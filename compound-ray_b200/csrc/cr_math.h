@@ -62,12 +62,12 @@ CR_HD void sincos(float x, float& sn, float& cs)
     float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
     pc = fmaf(z, pc, 4.166664568298827e-2f);
     const float c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
-    switch (k & 3) {
-        case 0: sn = s; cs = c; break;
-        case 1: sn = c; cs = -s; break;
-        case 2: sn = -s; cs = -c; break;
-        default: sn = -c; cs = s; break;
-    }
+    // quadrant k & 3: (sn, cs) = (s, c), (c, -s), (-s, -c), (-c, s) -- written as selects and sign flips (no branch: the lanes
+    // of a warp fall into different quadrants); a sign flip is exact, so the bits are those of the four-way switch
+    const bool swap = (k & 1) != 0;
+    const float a = swap ? c : s, b = swap ? s : c;
+    sn = (k & 2) ? -a : a;
+    cs = ((k + 1) & 2) ? -b : b;
 }
 
 CR_HD float log(float x)

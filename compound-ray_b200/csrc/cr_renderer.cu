@@ -63,6 +63,14 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_REDUCE")) fusedReduce = (std::string(e) == "fused" || std::string(e) == "1");
     if (const char* e = getenv("CR_FAST_MATH")) fastMath = atoi(e) != 0;
     if (const char* e = getenv("CR_CANDIDATE_LISTS")) candidateLists = atoi(e);
+    if (const char* e = getenv("CR_ZERO_COPY")) zeroCopyFrames = atoi(e) != 0;
+    if (const char* e = getenv("CR_DYNAMIC_CHUNKS")) dynamicChunks = atoi(e) != 0;
+    if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
+    if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
+    if (const char* e = getenv("CR_NODE_LANES")) nodeLanes = atoi(e);
+    if (const char* e = getenv("CR_WAVEFRONT")) wavefront = atoi(e);
+    if (const char* e = getenv("CR_WAVEFRONT_REFILL")) wavefrontRefill = atoi(e);
+    if (const char* e = getenv("CR_QUEUE_FRACTION")) queueFraction = atof(e);
 }
 Renderer::~Renderer()
 {
@@ -123,6 +131,8 @@ void Renderer::freeCompound(CompoundState& cs)
     dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
     dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries); dfree(cs.dPartials); dfree(cs.dLists);
+    dfree(cs.dQueueRays); dfree(cs.dQueueHits); dfree(cs.dQueueWarps); dfree(cs.dQueueCounters);
+    cs.queueCap = 0;
     cs.entryCap = 0;
     cs.listCap = 0;
     cs.entriesValid = false;
@@ -466,10 +476,83 @@ void Renderer::ensurePartials(CompoundState& cs, size_t frames)
     cs.partialCap = need;
 }
 
-void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow, int fastRowCount)
+// Wavefront queue: sized for `queueFraction` of the rays of a launch of `frames` frames (48 B per ray: origin, direction,
+// id and the hit record).  Warps that find it full walk their rays inline, so the size is a performance knob only.
+size_t Renderer::queueRaysFor(const CompoundState& cs, size_t frames) const
+{
+    const double rays = static_cast<double>(frames) * static_cast<double>(cs.N) * static_cast<double>(cs.S);
+    return static_cast<size_t>(std::min(rays * std::max(0.0, std::min(1.0, queueFraction)) + 32.0, 2.0e9)) & ~size_t(31);
+}
+
+void Renderer::ensureQueue(CompoundState& cs, size_t frames)
+{
+    const size_t need = queueRaysFor(cs, frames);
+    if (!cs.dQueueCounters) {
+        cs.dQueueCounters = dallocT<unsigned>(4);
+        CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 4, stream_));
+    }
+    if (cs.queueCap >= need && cs.dQueueRays) return;
+    dfree(cs.dQueueRays); dfree(cs.dQueueHits); dfree(cs.dQueueWarps);
+    cs.dQueueRays = dallocT<float4>(2 * need);
+    cs.dQueueHits = dallocT<int4>(need);
+    cs.dQueueWarps = dallocT<int>(need / 32 + 1);
+    cs.queueCap = need;
+}
+
+// The queue takes the warp-frames that have no candidate list, so it exists only in launches that build the lists.
+void Renderer::attachQueue(CompoundState& cs, EyeParams& ep)
+{
+    // counters: [0] rays pushed to the queue, [1] rays handed out by k_traceQueue (zeroed per launch that has a queue);
+    // [2] work chunks handed out, [3] warps that left the trace kernel (zeroed once: the kernel rearms them itself)
+    if (!cs.dQueueCounters) {
+        cs.dQueueCounters = dallocT<unsigned>(4);
+        CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 4, stream_));
+    }
+    if (dynamicChunks) ep.workCounter = cs.dQueueCounters + 2;
+    ep.chunkUnits = std::max(1, chunkUnits);
+    if (!wavefront || ep.lists == nullptr || dumpRays) return;
+    if (static_cast<double>(ep.poses ? ep.nFrames : 1) * cs.N >= 2147483648.0) return;   // frame*N + ommatidium would not fit 31 bits
+    ensureQueue(cs, ep.poses ? static_cast<size_t>(ep.nFrames) : 1);
+    CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 2, stream_));
+    ep.queueRays = cs.dQueueRays;
+    ep.queueHits = cs.dQueueHits;
+    ep.queueWarps = cs.dQueueWarps;
+    ep.queueCounters = cs.dQueueCounters;
+    ep.queueCap = static_cast<unsigned>(std::min(cs.queueCap, queueRaysFor(cs, ep.poses ? static_cast<size_t>(ep.nFrames) : 1)));
+    lastQueueCap_ = ep.queueCap;
+    ep.queueRefillBelow = std::max(1, std::min(32, wavefrontRefill));
+    launches_ += 2;   // k_traceQueue + k_shadeQueue
+}
+
+// Device-side breakdown of the last renderFrame of a compound eye (crDebugSetFrameProfile(1) first): milliseconds between the
+// event marks [frontier pass + counter reset, trace kernel(s), reduction kernel].
+void Renderer::debugFrameBreakdown(float* out3)
+{
+    out3[0] = out3[1] = out3[2] = -1.0f;
+    if (!profileFrame || !evMark_[3]) return;
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < 3; i++) cudaEventElapsedTime(out3 + i, evMark_[i], evMark_[i + 1]);
+}
+
+unsigned long long Renderer::debugLastQueuedRays()
+{
+    if (!compoundActive()) return 0;
+    CompoundState& cs = compoundState(current_);
+    if (!cs.dQueueCounters) return 0;
+    unsigned c[4] = {0, 0, 0, 0};
+    CR_CUDA(cudaMemcpyAsync(c, cs.dQueueCounters, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));
+    return std::min<unsigned long long>(c[0], lastQueueCap_);
+}
+
+void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow, int fastRowCount,
+                              uchar4* fastRowHost)
 {
     EyeParams ep;
+    ep.fastRowHost = fastRowHost;
     ep.fast = fastMath;
+    ep.nodeLanes = std::max(1, std::min(32, nodeLanes));
+    ep.entryMaxLevels = std::max(1, entryMaxLevels);
     if (fusedActive(cs, cam)) {
         ensurePartials(cs, 1);
         ep.fused = true;
@@ -496,9 +579,16 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
         }
         ep.dumpOrigins = cs.dDumpO; ep.dumpDirs = cs.dDumpD; ep.dumpHits = cs.dDumpH; ep.dumpCounts = cs.dDumpC;
     }
+    if (profileFrame) {
+        for (auto& e : evMark_) if (!e) CR_CUDA(cudaEventCreate(&e));
+        CR_CUDA(cudaEventRecord(evMark_[0], stream_));
+    }
     buildEntries(cs, ep);
+    attachQueue(cs, ep);
+    if (profileFrame) CR_CUDA(cudaEventRecord(evMark_[1], stream_));
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;   // persistent grid: every SM full
-    launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
+    launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_, profileFrame ? evMark_[2] : nullptr);
+    if (profileFrame) CR_CUDA(cudaEventRecord(evMark_[3], stream_));
     launches_ += 2;   // trace + ordered sum
     cs.frameIndex++;
     cs.dLastSummed = cs.dSummed;
@@ -509,6 +599,8 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
 {
     EyeParams ep;
     ep.fast = fastMath;
+    ep.nodeLanes = std::max(1, std::min(32, nodeLanes));
+    ep.entryMaxLevels = std::max(1, entryMaxLevels);
     if (dSamples == nullptr) {             // fused reduction: the caller sized cs.dPartials for nFrames
         ep.fused = true;
         ep.partials = cs.dPartials;
@@ -524,6 +616,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     ep.nFrames = nFrames;
     ep.poses = dPoses;
     buildEntries(cs, ep);
+    attachQueue(cs, ep);
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;
@@ -573,8 +666,11 @@ void Renderer::ensureFrame()
     hFrame_ = nullptr;
     dFrame_ = dallocT<uchar4>(need);
     CR_CUDA(cudaMemsetAsync(dFrame_, 0, sizeof(uchar4) * (need ? need : 1), stream_));
-    CR_CUDA(cudaMallocHost(&hFrame_, sizeof(uchar4) * (need ? need : 1)));
+    CR_CUDA(cudaHostAlloc(&hFrame_, sizeof(uchar4) * (need ? need : 1), cudaHostAllocMapped));
     memset(hFrame_, 0, sizeof(uchar4) * (need ? need : 1));
+    hFrameDev_ = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&hFrameDev_), hFrame_, 0) != cudaSuccess) { hFrameDev_ = nullptr; cudaGetLastError(); }
+    hostMirrorsDevice_ = true;                        // both all zero
     frameCap_ = need;
     frameW_ = W_;
     frameH_ = H_;
@@ -596,18 +692,24 @@ double Renderer::renderFrame()
     ensureFrame();
     HostCamera& cam = camera();
     const auto t0 = std::chrono::steady_clock::now();
-    bool timedTrace = false;
+    bool timedTrace = false, eager = false, zeroCopy = false;
     if (cam.kind == CAM_COMPOUND) {
         CompoundState& cs = compoundState(current_);
         prepareCompound(cs, cam);
         if (wantTraceEvents_) CR_CUDA(cudaEventRecord(evA_, stream_));
         // single_dimension_fast: pixel x of row 0 is ommatidium x -- K1b writes the row itself
         const bool fused = projectionFromName(cam.projection) == PROJ_SINGLE_DIM_FAST && W_ > 0 && H_ > 0;
-        launchCompound(cs, cam, cam.pose, fused ? dFrame_ : nullptr, fused ? std::min(cs.N, W_) : 0);
+        // ... and when the caller reads every frame (eager copy below) and the pinned host frame already equals the device
+        // frame everywhere else, K1b writes the row into the host frame as well: no copy is queued behind it
+        eager = frameWasFetched_ && sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
+        zeroCopy = fused && eager && hostMirrorsDevice_ && hFrameDev_ != nullptr && zeroCopyFrames && fusedActive(cs, cam);   // (k_sumPartials stores 128-byte rows)
+        launchCompound(cs, cam, cam.pose, fused ? dFrame_ : nullptr, fused ? std::min(cs.N, W_) : 0,
+                       zeroCopy ? reinterpret_cast<uchar4*>(hFrameDev_) : nullptr);
         if (wantTraceEvents_) CR_CUDA(cudaEventRecord(evB_, stream_));
         timedTrace = wantTraceEvents_;
         if (!fused) project(cs, cam);
     } else {
+        eager = frameWasFetched_ && sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
         launchCamera(dscene_, static_cast<int>(cam.kind), fastMath, toDevicePose(cam.pose), cam.scale[0], cam.scale[1], cam.scale[2], dFrame_,
                      W_, H_, stream_);
         launches_++;
@@ -615,9 +717,10 @@ double Renderer::renderFrame()
     // Small frames (eye vectors, thumbnails) ride back on the same stream, so the usual
     // renderFrame -> getFramePointer pair costs one synchronisation instead of two.  Callers that
     // did not read the previous frame (render-only timing loops) are not charged for the copy.
-    hostFrameFresh_ = frameWasFetched_ && sizeof(uchar4) * frameCap_ <= kEagerFrameBytes && frameCap_ > 0;
+    hostFrameFresh_ = eager;
     frameWasFetched_ = false;
-    if (hostFrameFresh_) CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
+    if (hostFrameFresh_ && !zeroCopy) CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
+    hostMirrorsDevice_ = hostFrameFresh_;             // after a copy or a dual write the two frames are equal again
     CR_CUDA(cudaStreamSynchronize(stream_));
     CR_CUDA(cudaGetLastError());
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -642,6 +745,7 @@ unsigned char* Renderer::framePointer()
     CR_CUDA(cudaMemcpyAsync(hFrame_, dFrame_, sizeof(uchar4) * frameCap_, cudaMemcpyDeviceToHost, stream_));
     CR_CUDA(cudaStreamSynchronize(stream_));
     hostFrameFresh_ = true;
+    hostMirrorsDevice_ = true;
     return hFrame_;
 }
 
@@ -735,6 +839,8 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
         cs.listCap = F * N;
         cs.entriesValid = false;
     }
+    if (wavefront && entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)))
+        ensureQueue(cs, F);
     if (cs.batchPoseCap < count) {
         dfree(cs.dBatchPoses);
         cs.dBatchPoses = dallocT<DevicePose>(count);

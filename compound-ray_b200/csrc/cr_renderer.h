@@ -44,6 +44,8 @@ struct CompoundState {                 // device side of one CompoundEye camera
     bool entriesValid = false; bool entriesLists = false; uint64_t entriesEyeVersion = 0;   // what dEntries/dLists row 0 was built for:
     DevicePose entriesPose{};                                                               // a single frame of this eye at this pose
     float4* dPartials = nullptr; size_t partialCap = 0;   // fused reduction: [frames][N][S/32] warp partials
+    // wavefront queue (k_traceCompound -> k_traceQueue -> k_shadeQueue): rays of the warp-frames without a candidate list
+    float4* dQueueRays = nullptr; int4* dQueueHits = nullptr; int* dQueueWarps = nullptr; unsigned* dQueueCounters = nullptr; size_t queueCap = 0;
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; int2* dDumpC = nullptr; size_t dumpCap = 0;
 };
@@ -84,6 +86,19 @@ public:
     bool fusedReduce = false;          // K1 sums 32 samples per warp in-kernel (fixed order, RGB equal to rounding) -- no sample buffer
     bool fastMath = false;             // hardware sin/cos/log/pow, as the reference's --use_fast_math build
     int candidateLists = 1;            // per-ommatidium candidate lists: 0 never, 1 in batches of >= 4 frames (default), 2 always
+    // Wavefront queue for the warp-frames that have no candidate list (they need the lists: same launches): 0 never
+    // (default since the trace kernel hands its units out dynamically: 23.2 vs 22.3 Grays/s with the queue), 1 in launches
+    // that build candidate lists, queueFraction = share of a launch's rays the queue is sized for
+    // (a warp that finds it full walks inline), wavefrontRefill = lanes below which k_traceQueue fetches new rays.
+    bool zeroCopyFrames = true;        // single_dimension_fast rows written straight into the pinned host frame (no D2H copy queued)
+    int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)
+    int chunkUnits = 1;                // single-frame trace kernel: units of 32 rays per counter fetch (larger chunks of one ommatidium's
+                                       // units measured slower: 2 -> 623, 4 -> 723, 8 -> 993 us per headline frame)
+    bool dynamicChunks = true;         // trace kernel: ray units handed out through a global counter instead of a static grid-stride split
+    int wavefront = 0;
+    int nodeLanes = 16;                // phase switch of the per-lane BVH walk (EyeParams::nodeLanes); 1 = classic while-while
+    int wavefrontRefill = 24;
+    double queueFraction = 0.35;
     int width() const { return W_; }
     int height() const { return H_; }
 
@@ -114,6 +129,9 @@ public:
     void debugCopyRngStates(uint32_t* out8);                      // [N*S][8] in reference stream-id order
     size_t debugCopyLastRayCounts(int32_t* counts2);
     size_t debugCopyCandidateLists(int32_t* out, size_t records);   // 16 ints per (frame, ommatidium) of the last launch
+    bool profileFrame = false;                                      // extra event marks inside renderFrame (debugFrameBreakdown)
+    void debugFrameBreakdown(float* out3);
+    unsigned long long debugLastQueuedRays();                       // rays the last trace launch sent through the wavefront queue
     size_t debugCopyLastRays(float* origins, float* dirs, int32_t* hits4);
     void debugTraceRays(const float* origins, const float* dirs, const float* tmins, int n, int32_t* hits8);
     void debugCopyProjectionMap(uint32_t* out);
@@ -126,11 +144,15 @@ private:
     void freeScene();
     CompoundState& compoundState(size_t camIdx);
     void prepareCompound(CompoundState& cs, HostCamera& cam);
-    void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow = nullptr, int fastRowCount = 0);
+    void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow = nullptr, int fastRowCount = 0,
+                        uchar4* fastRowHost = nullptr);
     void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
                              uchar4* fastRow = nullptr);
     bool fusedActive(const CompoundState& cs, const HostCamera& cam) const;
     void ensurePartials(CompoundState& cs, size_t frames);
+    void ensureQueue(CompoundState& cs, size_t frames);
+    size_t queueRaysFor(const CompoundState& cs, size_t frames) const;
+    void attachQueue(CompoundState& cs, EyeParams& ep);
     bool entryFrontierActive(const CompoundState& cs, int frames) const;   // frames = poses covered by the launch
     void buildEntries(CompoundState& cs, EyeParams& ep);
     void project(CompoundState& cs, const HostCamera& cam);
@@ -146,6 +168,7 @@ private:
     bool deviceReady_ = false;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evA_ = nullptr, evB_ = nullptr;
+    cudaEvent_t evMark_[4] = {nullptr, nullptr, nullptr, nullptr};
     int numSMs_ = 148;
     int traceOcc_ = 8;
 
@@ -165,7 +188,9 @@ private:
     std::map<size_t, CompoundState> compound_;
 
     uchar4* dFrame_ = nullptr;
-    unsigned char* hFrame_ = nullptr;                             // pinned
+    unsigned char* hFrame_ = nullptr;                             // pinned, mapped into the device address space
+    unsigned char* hFrameDev_ = nullptr;                          // device-side address of hFrame_
+    bool hostMirrorsDevice_ = false;                              // hFrame_ == dFrame_ byte for byte (after a full copy / both zero)
     size_t frameCap_ = 0;
     bool hostFrameFresh_ = false;                                 // hFrame_ already holds the last rendered frame
     bool frameWasFetched_ = true;                                 // the caller read the previous frame (getFramePointer/saveFrameAs)
@@ -179,6 +204,7 @@ private:
     double lastTraceMs_ = 0.0;
     bool wantTraceEvents_ = false;                                // renderFrame records its event pair only after crGetLastTraceMs was used
     int lastBatchFrames_ = 1;
+    unsigned lastQueueCap_ = 0;
     unsigned long long launches_ = 0;
 };
 

@@ -115,6 +115,13 @@ def configureFunctions(eyeRenderer):
     r.crSetRenderMode.argtypes = [C.c_int, C.c_int]
     r.crGetRenderMode.restype = C.c_int
     r.crDebugSetCandidateLists.argtypes = [C.c_int]
+    r.crDebugSetWavefront.argtypes = [C.c_int, C.c_int, C.c_double]
+    r.crDebugSetNodeLanes.argtypes = [C.c_int]
+    r.crDebugSetFrameProfile.argtypes = [C.c_int]
+    r.crDebugFrameBreakdown.argtypes = [vp]
+    r.crDebugSetDynamicChunks.argtypes = [C.c_int]
+    r.crDebugSetZeroCopy.argtypes = [C.c_int]
+    r.crDebugLastQueuedRays.restype = C.c_ulonglong
     r.crDebugCopyCandidateLists.argtypes = [vp, C.c_size_t]
     r.crDebugCopyCandidateLists.restype = C.c_size_t
     r.crGetLastBatchFrames.restype = C.c_int

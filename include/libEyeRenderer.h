@@ -205,6 +205,30 @@ void crDebugSetCandidateLists(int on);
  * frontier is walked per lane; 0: the cone reaches no leaf), [1..] = node << 2 | reachable-leaf mask.  Returns the
  * number of records copied (<= records; 0 when the launch built none). */
 size_t crDebugCopyCandidateLists(int32_t* out, size_t records);
+/* Wavefront queue (launches that build candidate lists): the warp-frames whose ommatidium has NO list -- cones that graze
+ * the scene, whose 32 per-lane walks drift far apart -- are not walked inside the trace kernel; their rays go to a queue,
+ * k_traceQueue traces it with dynamic ray fetch (a lane that finishes pulls the next ray) and k_shadeQueue shades and
+ * reduces them in the pushing warp's lane order.  Same hits, same output bits.  on: 0 never (default: with the trace
+ * kernel's dynamic work distribution the queue measured slower), 1 in launches that build candidate lists; refillBelow
+ * (1..32, <= 0 keeps it): lanes still walking below which a warp fetches new rays; queueFraction (< 0 keeps it): share
+ * of a launch's rays the queue is sized for -- warps that find it full walk inline. */
+void crDebugSetWavefront(int on, int refillBelow, double queueFraction);
+/* Phase switch of the per-lane BVH walk (trace kernel and k_traceQueue): the warp leaves its node loop for the pending
+ * leaves as soon as fewer than `lanes` (1..32) lanes still want a node; 1 = classic while-while (a lane at a leaf waits
+ * for every other lane).  Each lane's own sequence of node and triangle tests does not change: same hits. */
+void crDebugSetNodeLanes(int lanes);
+/* Device-side breakdown of renderFrame for a compound eye: with the profile on, event marks are recorded inside the frame
+ * and crDebugFrameBreakdown returns the milliseconds of [frontier pass (+ counter reset), trace kernel(s), reduction kernel]
+ * of the last frame (-1 when there is none). */
+void crDebugSetFrameProfile(int on);
+void crDebugFrameBreakdown(float* out3);
+/* Trace kernel work distribution: 1 (default) = units of 32 rays handed out through a global counter, 0 = static
+ * grid-stride split.  Which warp traces a ray does not enter its result. */
+void crDebugSetDynamicChunks(int on);
+/* single_dimension_fast rows written by the reduction kernel straight into the pinned (mapped) host frame when the caller
+ * reads every frame: 1 (default) on, 0 = always a device-to-host copy behind the frame's kernels.  Same bytes. */
+void crDebugSetZeroCopy(int on);
+unsigned long long crDebugLastQueuedRays(void);  /* rays of the last trace launch that went through the queue */
 size_t crDebugCopyLastRays(float* origins3, float* dirs3, int32_t* hits4);  /* stream-id order N*s+o */
 size_t crDebugCopyLastRayCounts(int32_t* counts2); /* (BVH nodes fetched, triangles tested) per dumped ray, same order */
 void crDebugCopyRngStates(uint32_t* out8);       /* d, v0..v4, flag, extra bits; stream-id order */

@@ -34,6 +34,9 @@ def _default_modes(lib):
     yield
     lib.crSetRenderMode(0, 0)
     lib.crDebugSetCandidateLists(2)
+    lib.crDebugSetWavefront(0, 24, 0.35)
+    lib.crDebugSetNodeLanes(16)
+    lib.crDebugSetDynamicChunks(1)
     lib.crDebugSetRayDump(False)
     lib.crDebugSetEntryFrontier(1, 2, 0)
     lib.crSetFirstFrame(0)
@@ -165,6 +168,60 @@ def test_candidate_lists_stress_eye_and_batches(lib, er, terrain):
     assert np.array_equal(res[0][1], res[1][1]), "batch rows"
     assert used >= len(poses) // 2, "the candidate lists were hardly used"
     assert sum((f[1]["prim"] >= 0).sum() for f in res[0][0]) > 10000
+
+
+def test_wavefront_queue_changes_no_bit(lib, er, loader, oracle, terrain):
+    """The warp-frames without a candidate list go through the wavefront queue (k_traceQueue with dynamic ray fetch,
+    k_shadeQueue) instead of the per-lane walk inside the trace kernel, and both walks switch between their node and leaf
+    phases on a lane-count vote (crDebugSetNodeLanes; 1 = classic while-while): per-ommatidium float RGB, 8-bit rows and
+    batch rows are bit-identical with the queue off, on, on with other refill and phase thresholds, and with a queue so
+    small that most warps find it full and walk inline -- in the ordered and in the fused reduction, per frame and batched,
+    with the trace kernel's units handed out by the work counter or by the static grid-stride split; and equal the oracle."""
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    sc, sh, ocam = load_oracle_scene(loader, oracle, terrain, "compound-cam")
+    N, S = 2500, 64
+    omm = ocam.ommatidia[:: len(ocam.ommatidia) // N][:N]
+    er.setOmmatidiaFromArray(lib, omm)
+    er.setRenderSize(lib, N, 1)
+    eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+    eye.set_render_size(N, 1)
+    eye.render_frame(method="bvh")
+    want_seq, want_fused = eye.last["summed"].copy(), oracle.fused_sum(eye.last["compound"], N, S)
+    pose0 = np.zeros(12, np.float32); lib.crDebugCopyCameraPose(pose0.ctypes.data)
+    poses = np.tile(pose0, (6, 1)); poses[:, 1] += np.float32([0.0, 0.25, 0.5, 1.0, 3.0, 9.0])
+    out = {}
+    for fused in (0, 1):
+        for key, (on, refill, frac, lanes) in {"off": (0, 24, 0.35, 1), "static": (0, 24, 0.35, 16), "off32": (0, 24, 0.35, 32),
+                                               "on": (1, 24, 0.35, 16), "refill32": (1, 32, 0.35, 24), "refill1": (1, 1, 0.35, 1),
+                                               "tiny": (1, 24, 0.002, 32)}.items():
+            lib.crSetRenderMode(fused, 0)
+            lib.crDebugSetDynamicChunks(0 if key in ("static", "refill1") else 1)     # static grid-stride split vs the work counter
+            lib.crDebugSetNodeLanes(lanes)
+            lib.crDebugSetWavefront(on, refill, frac)
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            lib.renderFrame()
+            queued = lib.crDebugLastQueuedRays()
+            rgb = er.getOmmatidialData(lib).copy()
+            row = er.getFrame(lib, N, 1).copy()
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            rows, _ = er.renderPoseBatch(lib, poses)
+            queued_batch = lib.crDebugLastQueuedRays()
+            out[(fused, key)] = (rgb, row, rows.copy())
+            if on:
+                assert queued > 0 and queued % 32 == 0 and queued_batch > 0, (key, queued, queued_batch)
+                if key == "tiny":
+                    assert queued <= 0.002 * N * S + 32
+                else:
+                    assert 0.02 * N * S < queued < 0.35 * N * S, (key, queued)
+            want = want_fused if fused else want_seq
+            assert np.array_equal(rgb.view(np.uint32), want.view(np.uint32)), (fused, key)
+        for key in ("static", "off32", "on", "refill32", "refill1", "tiny"):
+            for a, b in zip(out[(fused, "off")], out[(fused, key)]):
+                assert np.array_equal(a, b), (fused, key)
+        assert np.array_equal(out[(fused, "off")][1][0], out[(fused, "off")][2][0])
+    lib.crSetRenderMode(0, 0)
 
 
 def test_fused_reduction_fixed_order_and_tolerance(lib, er, loader, oracle, terrain):
