@@ -67,6 +67,8 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_DYNAMIC_CHUNKS")) dynamicChunks = atoi(e) != 0;
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
+    if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
+    if (const char* e = getenv("CR_SPIN_SYNC")) spinSync = atoi(e) != 0;
     if (const char* e = getenv("CR_NODE_LANES")) nodeLanes = atoi(e);
     if (const char* e = getenv("CR_WAVEFRONT")) wavefront = atoi(e);
     if (const char* e = getenv("CR_WAVEFRONT_REFILL")) wavefrontRefill = atoi(e);
@@ -101,6 +103,7 @@ void Renderer::ensureDevice()
         device_ = env ? atoi(env) : 0;
     }
     if (device_ >= count) throw std::runtime_error("requested CUDA device index out of range");
+    if (spinSync) { if (cudaSetDeviceFlags(cudaDeviceScheduleSpin) != cudaSuccess) cudaGetLastError(); }   // (before the context exists)
     CR_CUDA(cudaSetDevice(device_));
     CR_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CR_CUDA(cudaEventCreate(&evA_));
@@ -421,7 +424,15 @@ bool Renderer::entryFrontierActive(const CompoundState& cs, int frames) const
 void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
 {
     cs.listsLast = 0;
-    if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1)) return;
+    // Frames too small to amortise the pass get the frontier all the same once the camera has stood still for three
+    // frames (the reference's speed-test and variance protocols: hundreds of frames from one pose): built once, then reused.
+    const bool standing = ep.poses == nullptr && cs.lastPoseValid && cs.lastPoseEyeVersion == cs.eyeVersion &&
+                          memcmp(&cs.lastPose, &ep.pose, sizeof(DevicePose)) == 0;
+    cs.standingFrames = standing ? cs.standingFrames + 1 : 0;
+    cs.lastPoseValid = ep.poses == nullptr;
+    cs.lastPose = ep.pose;
+    cs.lastPoseEyeVersion = cs.eyeVersion;
+    if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1) && !(entryFrontier && standingFrontier && cs.N > 0 && cs.standingFrames >= 2)) return;
     const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(ep.poses ? ep.nFrames : 1);
     if (cs.entryCap < need) {
         dfree(cs.dEntries);

@@ -42,6 +42,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     int* dLists = nullptr; size_t listCap = 0;       // candidate lists [frames][N][16] (k_buildEntries stage 2)
     size_t listsLast = 0;                            // records written by the last launch (0: lists not built)
     bool entriesValid = false; bool entriesLists = false; uint64_t entriesEyeVersion = 0;   // what dEntries/dLists row 0 was built for:
+    bool lastPoseValid = false; DevicePose lastPose{}; uint64_t lastPoseEyeVersion = 0; int standingFrames = 0;   // consecutive single frames from one pose
     DevicePose entriesPose{};                                                               // a single frame of this eye at this pose
     float4* dPartials = nullptr; size_t partialCap = 0;   // fused reduction: [frames][N][S/32] warp partials
     // wavefront queue (k_traceCompound -> k_traceQueue -> k_shadeQueue): rays of the warp-frames without a candidate list
@@ -91,6 +92,8 @@ public:
     // that build candidate lists, queueFraction = share of a launch's rays the queue is sized for
     // (a warp that finds it full walks inline), wavefrontRefill = lanes below which k_traceQueue fetches new rays.
     bool zeroCopyFrames = true;        // single_dimension_fast rows written straight into the pinned host frame (no D2H copy queued)
+    bool standingFrontier = true;      // small frames: build the frontier once the camera has stood still for three frames, then reuse it
+    bool spinSync = false;             // cudaDeviceScheduleSpin (CR_SPIN_SYNC=1, before the first GPU use)
     int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)
     int chunkUnits = 1;                // single-frame trace kernel: units of 32 rays per counter fetch (larger chunks of one ommatidium's
                                        // units measured slower: 2 -> 623, 4 -> 723, 8 -> 993 us per headline frame)
