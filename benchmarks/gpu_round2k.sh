@@ -1,18 +1,12 @@
 #!/bin/bash
-# K0b on the cone axis's node copy; frontier depth cap sweep.
+# Read-ahead for standing cameras: tests + speed-test protocol + bench sanity.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r02q}
+T=${TAG:-r02t}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_modes.py tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"
-tail -3 gpurun_out/${T}_tests.log
-run() { # name, env...
-  name=$1; shift
-  env "$@" timeout 600 python benchmarks/wavefront_sweep.py --modes 1:0 --refills 12 --node-lanes 8 --inline-lanes ${NL:-16} --out gpurun_out/${T}_ab_${name}.json > gpurun_out/${T}_ab_${name}.log 2>&1; echo "$name rc=$?"
-}
-run default CR_X=1
-run lev20 CR_ENTRY_MAX_LEVELS=20
-run lev16 CR_ENTRY_MAX_LEVELS=16
-run lev13 CR_ENTRY_MAX_LEVELS=13
-run lev10 CR_ENTRY_MAX_LEVELS=10
-run default2 CR_X=1
-ls gpurun_out | grep ${T}
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/${T}_gpu_tests.log 2>&1; echo "all gpu tests rc=$?"
+tail -12 gpurun_out/${T}_gpu_tests.log
+timeout 600 python benchmarks/speed_test.py > gpurun_out/${T}_speed_test_protocol.txt 2>&1; echo "speed test rc=$?"
+CR_READ_AHEAD=0 timeout 600 python benchmarks/speed_test.py --samples 1,8,32,128,1000,3200 --frames 300 > gpurun_out/${T}_speed_test_noreadahead.txt 2>&1; echo "speed test (no read-ahead) rc=$?"
+grep -h "^ *S=" gpurun_out/${T}_speed_test_protocol.txt gpurun_out/${T}_speed_test_noreadahead.txt | cut -c1-100
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-modes > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.log; echo "bench rc=$?"
+python -c "import json;d=json.load(open('gpurun_out/${T}_bench.json'));print(d['value']/1e9, d['e2e']['value']/1e9)"

@@ -378,6 +378,11 @@ void crDebugSetWavefront(int on, int refillBelow, double queueFraction)
     if (queueFraction >= 0.0) renderer().queueFraction = queueFraction;
 }
 void crDebugSetNodeLanes(int lanes) { renderer().nodeLanes = lanes; }
+void crDebugSetReadAhead(int on, double budgetMs)
+{
+    renderer().readAhead = on != 0;
+    if (budgetMs > 0.0) renderer().readAheadBudgetMs = budgetMs;
+}
 void crDebugSetFrameProfile(int on) { renderer().profileFrame = on != 0; }
 void crDebugFrameBreakdown(float* out3)
 {

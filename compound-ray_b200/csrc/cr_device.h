@@ -83,6 +83,7 @@ struct EyeParams {
     int fastRowCount = 0;
     uchar4* fastRowHost = nullptr;       // when set: the same pixels also go straight to the mapped pinned host frame
     const int4* entries = nullptr;       // [nFrames][N] entry frontier (k_buildEntries); nullptr: start at the root
+    unsigned entryFrameStride = 0;       // rows between the frames of `entries` / `lists`: N, or 0 when every frame of the launch has the same pose
     // wavefront queue of the warp-frames whose ommatidium has no candidate list (k_traceCompound -> k_traceQueue -> k_shadeQueue)
     float4* queueRays = nullptr;         // 2 float4 per ray: (origin, tmin), (direction, frame*N + ommatidium | inCone << 31)
     int* queueWarps = nullptr;           // per 32 queue slots (one pushed warp-frame): its block of 32 samples within the row

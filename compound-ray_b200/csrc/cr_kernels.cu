@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
             const int* list = nullptr;
             int listN = kListFallback;
             if (warpRows && ep.lists != nullptr) {
-                list = ep.lists + ((size_t)f * (unsigned)ep.N + o) * kListStride;
+                list = ep.lists + ((size_t)f * ep.entryFrameStride + o) * kListStride;
                 listN = __ldg(list);
                 if (listN != kListFallback && !__all_sync(kFullMask, inCone)) listN = kListFallback;
             }
@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 }
                 if (!queued) {
                     int4 entry = make_int4(0, kSentinel, kSentinel, kSentinel);
-                    if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * (unsigned)ep.N + o);
+                    if (ep.entries != nullptr && inCone) entry = __ldg(ep.entries + (size_t)f * ep.entryFrameStride + o);
 #if CR_INLINE_PHASED
                     h = traceClosestPhased<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
                                                  &nNode, &nTri, entry, ep.nodeLanes);

@@ -68,6 +68,8 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
     if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
+    if (const char* e = getenv("CR_READ_AHEAD")) readAhead = atoi(e) != 0;
+    if (const char* e = getenv("CR_READ_AHEAD_MS")) readAheadBudgetMs = atof(e);
     if (const char* e = getenv("CR_SPIN_SYNC")) spinSync = atoi(e) != 0;
     if (const char* e = getenv("CR_NODE_LANES")) nodeLanes = atoi(e);
     if (const char* e = getenv("CR_WAVEFRONT")) wavefront = atoi(e);
@@ -135,6 +137,14 @@ void Renderer::freeCompound(CompoundState& cs)
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
     dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries); dfree(cs.dPartials); dfree(cs.dLists);
     dfree(cs.dQueueRays); dfree(cs.dQueueHits); dfree(cs.dQueueWarps); dfree(cs.dQueueCounters);
+    dfree(cs.dAheadRows);
+    if (cs.hAheadRows) cudaFreeHost(cs.hAheadRows);
+    cs.hAheadRows = nullptr;
+    cs.aheadRowCap = 0;
+    cs.ahead = CompoundState::ReadAhead{};
+    cs.needRewind = false;
+    cs.lastPoseValid = false;
+    cs.standingFrames = 0;
     cs.queueCap = 0;
     cs.entryCap = 0;
     cs.listCap = 0;
@@ -353,6 +363,7 @@ void Renderer::setOmmatidialShard(uint64_t globalCount, uint64_t first)
 {
     if (!compoundActive()) return;
     CompoundState& cs = compoundState(current_);
+    dropReadAhead(cs);
     cs.shardGlobalN = globalCount;
     cs.shardFirst = globalCount ? first : 0;
     cs.randomsConfigured = false;
@@ -361,6 +372,7 @@ void Renderer::setFirstFrame(uint64_t k)
 {
     if (!compoundActive()) return;
     CompoundState& cs = compoundState(current_);
+    dropReadAhead(cs);
     cs.firstFrame = k;
     cs.randomsConfigured = false;
 }
@@ -398,6 +410,13 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
         cs.rngS = cs.S;
         cs.randomsConfigured = false;
     }
+    if (cs.needRewind) {                                 // frames rendered ahead were dropped: put the streams back where the caller is
+        if (cs.randomsConfigured) {                      // (a pending reset -- new S, new count, crSetFirstFrame -- supersedes the rewind)
+            cs.firstFrame = cs.rewindTo;
+            cs.randomsConfigured = false;
+        }
+        cs.needRewind = false;
+    }
     if (!cs.randomsConfigured) {
         const bool sharded = cs.shardGlobalN > 0;        // stream ids of an ommatidium-range shard use global indices
         if (!dJumpTable_) {                              // XORWOW jump-ahead matrices: derived once per process (~20 ms), 1.8 MB
@@ -426,13 +445,9 @@ void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
     cs.listsLast = 0;
     // Frames too small to amortise the pass get the frontier all the same once the camera has stood still for three
     // frames (the reference's speed-test and variance protocols: hundreds of frames from one pose): built once, then reused.
-    const bool standing = ep.poses == nullptr && cs.lastPoseValid && cs.lastPoseEyeVersion == cs.eyeVersion &&
-                          memcmp(&cs.lastPose, &ep.pose, sizeof(DevicePose)) == 0;
-    cs.standingFrames = standing ? cs.standingFrames + 1 : 0;
-    cs.lastPoseValid = ep.poses == nullptr;
-    cs.lastPose = ep.pose;
-    cs.lastPoseEyeVersion = cs.eyeVersion;
-    if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1) && !(entryFrontier && standingFrontier && cs.N > 0 && cs.standingFrames >= 2)) return;
+    // (cs.standingFrames: noteSinglePose, once per renderFrame)
+    if (!entryFrontierActive(cs, ep.poses ? ep.nFrames : 1) &&
+        !(entryFrontier && standingFrontier && ep.poses == nullptr && cs.N > 0 && cs.standingFrames >= 2)) return;
     const size_t need = static_cast<size_t>(cs.N) * static_cast<size_t>(ep.poses ? ep.nFrames : 1);
     if (cs.entryCap < need) {
         dfree(cs.dEntries);
@@ -467,8 +482,19 @@ void Renderer::buildEntries(CompoundState& cs, EyeParams& ep)
     cs.entriesLists = wantLists;
     cs.entriesPose = ep.pose;
     ep.entries = cs.dEntries;
+    ep.entryFrameStride = static_cast<unsigned>(cs.N);
     ep.lists = wantLists ? cs.dLists : nullptr;
     cs.listsLast = wantLists ? need : 0;
+}
+
+// Once per renderFrame of a compound eye: how many consecutive frames this camera has been rendered from one pose.
+void Renderer::noteSinglePose(CompoundState& cs, const DevicePose& pose)
+{
+    const bool standing = cs.lastPoseValid && cs.lastPoseEyeVersion == cs.eyeVersion && memcmp(&cs.lastPose, &pose, sizeof(DevicePose)) == 0;
+    cs.standingFrames = standing ? cs.standingFrames + 1 : 0;
+    cs.lastPoseValid = true;
+    cs.lastPose = pose;
+    cs.lastPoseEyeVersion = cs.eyeVersion;
 }
 
 // The in-kernel reduction needs whole warps per ommatidium (S % 32 == 0) and is bypassed where somebody reads the
@@ -606,7 +632,7 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
 }
 
 void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
-                                   uchar4* fastRow)
+                                   uchar4* fastRow, const Pose* samePose)
 {
     EyeParams ep;
     ep.fast = fastMath;
@@ -625,9 +651,24 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     ep.N = cs.N;
     ep.S = cs.S;
     ep.nFrames = nFrames;
-    ep.poses = dPoses;
-    buildEntries(cs, ep);
-    attachQueue(cs, ep);
+    if (samePose) {                         // every frame of the launch from one pose (read-ahead): ONE frontier row serves them all
+        ep.pose = toDevicePose(*samePose);
+        ep.nFrames = 1;
+        buildEntries(cs, ep);               // single-frame rules: reuses the standing camera's entries
+        ep.nFrames = nFrames;
+        ep.entryFrameStride = 0;
+        ep.poses = dPoses;
+        if (!cs.dQueueCounters) {
+            cs.dQueueCounters = dallocT<unsigned>(4);
+            CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 4, stream_));
+        }
+        if (dynamicChunks) ep.workCounter = cs.dQueueCounters + 2;
+        ep.chunkUnits = 1;
+    } else {
+        ep.poses = dPoses;
+        buildEntries(cs, ep);
+        attachQueue(cs, ep);
+    }
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;
@@ -704,9 +745,24 @@ double Renderer::renderFrame()
     HostCamera& cam = camera();
     const auto t0 = std::chrono::steady_clock::now();
     bool timedTrace = false, eager = false, zeroCopy = false;
+    CompoundState* singleCompound = nullptr;
     if (cam.kind == CAM_COMPOUND) {
         CompoundState& cs = compoundState(current_);
+        // standing camera: the next frame may already be there, or this call renders several at once
+        const bool aheadOk = readAheadEligible(cs, cam);
+        if (consumeReadAhead(cs, cam, aheadOk)) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (verbose) std::cout << "[PyEye] Rendered frame in " << ms << "ms." << std::endl;
+            return ms;
+        }
         prepareCompound(cs, cam);
+        noteSinglePose(cs, toDevicePose(cam.pose));
+        if (readAheadEligible(cs, cam) && launchReadAhead(cs, cam)) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (verbose) std::cout << "[PyEye] Rendered frame in " << ms << "ms." << std::endl;
+            return ms;
+        }
+        singleCompound = &cs;
         if (wantTraceEvents_) CR_CUDA(cudaEventRecord(evA_, stream_));
         // single_dimension_fast: pixel x of row 0 is ommatidium x -- K1b writes the row itself
         const bool fused = projectionFromName(cam.projection) == PROJ_SINGLE_DIM_FAST && W_ > 0 && H_ > 0;
@@ -735,6 +791,7 @@ double Renderer::renderFrame()
     CR_CUDA(cudaStreamSynchronize(stream_));
     CR_CUDA(cudaGetLastError());
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (singleCompound) singleCompound->lastSingleFrameMs = ms;
     if (timedTrace) {
         float k = 0.0f;
         cudaEventElapsedTime(&k, evA_, evB_);
@@ -793,6 +850,140 @@ void Renderer::copyOmmatidialData(float* outRgb)
     for (size_t i = 0; i < tmp.size(); i++) { outRgb[3 * i] = tmp[i].x; outRgb[3 * i + 1] = tmp[i].y; outRgb[3 * i + 2] = tmp[i].z; }
 }
 
+// Frames per batched launch: bounded by a sample-buffer budget in the ordered mode (12 B per ray per frame held between K1 and
+// K1b; the fused mode holds 0.5 B: one float4 per warp).
+size_t Renderer::batchFramesPerLaunch(const CompoundState& cs, size_t count, bool fused) const
+{
+    const size_t raysPerFrame = static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
+    size_t budget = size_t(4) << 30;   // 8 -> 16 -> 32 -> 64 frames per launch: 18.8 -> 19.3 -> 19.6 -> 19.9 Grays/s on the headline workload
+    if (const char* env = getenv("CR_BATCH_BYTES")) budget = static_cast<size_t>(atoll(env));
+    size_t F = std::max<size_t>(1, std::min<size_t>(count, fused ? size_t(256) : budget / std::max<size_t>(1, raysPerFrame * 12)));
+    if (const char* env = getenv("CR_BATCH_FRAMES")) F = std::max<size_t>(1, std::min<size_t>(count, static_cast<size_t>(atoll(env))));
+    return F;
+}
+
+void Renderer::ensureBatchBuffers(CompoundState& cs, size_t F, bool fused)
+{
+    const size_t N = static_cast<size_t>(cs.N);
+    const size_t raysPerFrame = N * static_cast<size_t>(cs.S);
+    if (fused) {
+        ensurePartials(cs, F);
+    } else if (cs.batchSampleCap < F * raysPerFrame * 3) {
+        dfree(cs.dBatchSamples);
+        cs.dBatchSamples = dallocT<float>(F * raysPerFrame * 3);
+        cs.batchSampleCap = F * raysPerFrame * 3;
+    }
+    if (cs.batchSummedCap < F * N) {
+        dfree(cs.dBatchSummed);
+        cs.dLastSummed = nullptr;
+        cs.dBatchSummed = dallocT<float4>(F * N);
+        CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
+        cs.batchSummedCap = F * N;
+    }
+    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.entryCap < F * N) {
+        dfree(cs.dEntries);
+        cs.dEntries = dallocT<int4>(F * N);
+        cs.entryCap = F * N;
+        cs.entriesValid = false;
+    }
+    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)) &&
+        cs.listCap < F * N) {
+        dfree(cs.dLists);
+        cs.dLists = dallocT<int>(F * N * static_cast<size_t>(candidateListStride()));
+        cs.listCap = F * N;
+        cs.entriesValid = false;
+    }
+    if (wavefront && entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)))
+        ensureQueue(cs, F);
+}
+
+// ------------------------------------------------------------------------------------------
+// Read-ahead for a standing camera (see cr_renderer.h).  The frames of a batched launch equal the frames of as many
+// renderFrame calls bit for bit (same kernel body, same streams), so handing them out one per call changes nothing but
+// when they are rendered.
+// ------------------------------------------------------------------------------------------
+bool Renderer::readAheadEligible(const CompoundState& cs, const HostCamera& cam) const
+{
+    return readAhead && !dumpRays && !profileFrame && cs.randomsConfigured && W_ > 0 && H_ > 0 &&
+           projectionFromName(cam.projection) == PROJ_SINGLE_DIM_FAST && cs.N > 0 &&
+           static_cast<long long>(cs.N) * cs.S <= readAheadMaxRays;
+}
+
+void Renderer::dropReadAhead(CompoundState& cs)
+{
+    if (cs.ahead.count > cs.ahead.next) {                // the streams ran ahead of the caller: rewind at the next prepareCompound
+        cs.needRewind = true;
+        cs.rewindTo = cs.frameIndex;
+    }
+    cs.ahead.count = cs.ahead.next = 0;
+}
+
+// Hands out the next frame rendered ahead, if there is one and nothing it depends on has changed.
+bool Renderer::consumeReadAhead(CompoundState& cs, const HostCamera& cam, bool eligible)
+{
+    CompoundState::ReadAhead& a = cs.ahead;
+    if (a.count <= a.next) return false;
+    const DevicePose pose = toDevicePose(cam.pose);
+    const bool same = eligible && a.eyeVersion == cs.eyeVersion && a.S == cs.S && a.N == static_cast<int>(cam.ommatidia.size()) &&
+                      a.fused == fusedActive(cs, cam) && a.fast == fastMath && a.rowPixels == std::min(cs.N, W_) &&
+                      memcmp(&a.pose, &pose, sizeof(DevicePose)) == 0;
+    if (!same) { dropReadAhead(cs); return false; }
+    const size_t f = static_cast<size_t>(a.next++);
+    memcpy(hFrame_, cs.hAheadRows + sizeof(uchar4) * f * static_cast<size_t>(cs.N), sizeof(uchar4) * static_cast<size_t>(a.rowPixels));
+    hostFrameFresh_ = true;                              // the pinned host frame holds this frame; the device frame does not
+    hostMirrorsDevice_ = false;
+    frameWasFetched_ = false;
+    cs.frameIndex++;
+    cs.dLastSummed = cs.dBatchSummed + f * static_cast<size_t>(cs.N);
+    lastTraceMs_ = a.traceMsPerFrame;
+    noteSinglePose(cs, pose);
+    return true;
+}
+
+// Renders the next frames of a standing camera in one batched launch and hands out the first.  False: not worth it / not
+// possible now (the caller renders one frame the usual way).
+bool Renderer::launchReadAhead(CompoundState& cs, const HostCamera& cam)
+{
+    if (cs.standingFrames < 2 || cs.lastSingleFrameMs <= 0.0) return false;
+    const bool fused = fusedActive(cs, cam);
+    size_t F = static_cast<size_t>(std::min(64.0, readAheadBudgetMs / std::max(cs.lastSingleFrameMs, 1e-3)));
+    F = std::min(F, batchFramesPerLaunch(cs, F, fused));
+    if (F < 2) return false;
+    const size_t N = static_cast<size_t>(cs.N);
+    ensureBatchBuffers(cs, F, fused);
+    if (cs.aheadRowCap < F * N) {
+        dfree(cs.dAheadRows);
+        if (cs.hAheadRows) cudaFreeHost(cs.hAheadRows);
+        cs.dAheadRows = dallocT<uchar4>(F * N);
+        CR_CUDA(cudaMallocHost(&cs.hAheadRows, sizeof(uchar4) * F * N));
+        cs.aheadRowCap = F * N;
+    }
+    if (cs.batchPoseCap < F) {
+        dfree(cs.dBatchPoses);
+        cs.dBatchPoses = dallocT<DevicePose>(F);
+        cs.batchPoseCap = F;
+    }
+    const DevicePose dp = toDevicePose(cam.pose);
+    std::vector<DevicePose> hPoses(F, dp);
+    CR_CUDA(cudaMemcpyAsync(cs.dBatchPoses, hPoses.data(), sizeof(DevicePose) * F, cudaMemcpyHostToDevice, stream_));
+    const uint64_t frame0 = cs.frameIndex;
+    CR_CUDA(cudaEventRecord(evA_, stream_));
+    launchCompoundBatch(cs, cs.dBatchPoses, static_cast<int>(F), fused ? nullptr : cs.dBatchSamples, cs.dBatchSummed, cs.dAheadRows, &cam.pose);
+    CR_CUDA(cudaEventRecord(evB_, stream_));
+    CR_CUDA(cudaMemcpyAsync(cs.hAheadRows, cs.dAheadRows, sizeof(uchar4) * F * N, cudaMemcpyDeviceToHost, stream_));
+    CR_CUDA(cudaStreamSynchronize(stream_));             // (hPoses must outlive the copy)
+    CR_CUDA(cudaGetLastError());
+    cs.frameIndex = frame0;                              // the caller has consumed none of them yet
+    float k = 0.0f;
+    cudaEventElapsedTime(&k, evA_, evB_);
+    CompoundState::ReadAhead& a = cs.ahead;
+    a.count = static_cast<int>(F); a.next = 0;
+    a.rowPixels = std::min(cs.N, W_); a.S = cs.S; a.N = cs.N;
+    a.pose = dp; a.eyeVersion = cs.eyeVersion; a.fused = fused; a.fast = fastMath;
+    a.traceMsPerFrame = static_cast<double>(k) / static_cast<double>(F);
+    return consumeReadAhead(cs, cam, true);
+}
+
 // Renders `count` consecutive frames of the current compound eye, one per pose (12 floats each:
 // position, x, y, z axes), exactly as `count` calls of setCameraPosition/LocalSpace + renderFrame
 // would, but without per-frame host synchronisation.  Row p of the result is the
@@ -808,50 +999,19 @@ double Renderer::renderPoseBatch(const float* poses12, size_t count, unsigned ch
     HostCamera& cam = camera();
     CompoundState& cs = compoundState(current_);
     const auto t0 = std::chrono::steady_clock::now();
+    dropReadAhead(cs);                                   // frames rendered ahead for renderFrame: the batch continues where the CALLER is
+    cs.lastPoseValid = false;
+    cs.standingFrames = 0;
     prepareCompound(cs, cam);
     const size_t N = static_cast<size_t>(cs.N);
     uchar4* dOut = static_cast<uchar4*>(outDevice);
     uchar4* dTmp = nullptr;
     if (!dOut) { dTmp = dallocT<uchar4>(N * count); dOut = dTmp; }
-    // frames per launch: bounded by a sample-buffer budget (12 B per ray per frame)
-    const size_t raysPerFrame = N * static_cast<size_t>(cs.S);
     const bool fused = fusedReduce && cs.S % 32 == 0 && !dumpRays;
-    size_t budget = size_t(4) << 30;   // 8 -> 16 -> 32 -> 64 frames per launch: 18.8 -> 19.3 -> 19.6 -> 19.9 Grays/s on the headline workload
-    if (const char* env = getenv("CR_BATCH_BYTES")) budget = static_cast<size_t>(atoll(env));
-    // bytes per ray and frame held between K1 and K1b: 12 (ordered: one float3 per sample) or 0.5 (fused: one float4 per warp)
-    size_t F = std::max<size_t>(1, std::min<size_t>(count, fused ? size_t(256) : budget / std::max<size_t>(1, raysPerFrame * 12)));
-    if (const char* env = getenv("CR_BATCH_FRAMES")) F = std::max<size_t>(1, std::min<size_t>(count, static_cast<size_t>(atoll(env))));
+    size_t F = batchFramesPerLaunch(cs, count, fused);
     if (dumpRays) F = 1;
     lastBatchFrames_ = static_cast<int>(F);
-    if (fused) {
-        ensurePartials(cs, F);
-    } else if (cs.batchSampleCap < F * raysPerFrame * 3) {
-        dfree(cs.dBatchSamples);
-        cs.dBatchSamples = dallocT<float>(F * raysPerFrame * 3);
-        cs.batchSampleCap = F * raysPerFrame * 3;
-    }
-    if (cs.batchSummedCap < F * N) {
-        dfree(cs.dBatchSummed);
-        cs.dLastSummed = nullptr;
-        cs.dBatchSummed = dallocT<float4>(F * N);
-        CR_CUDA(cudaMemsetAsync(cs.dBatchSummed, 0, sizeof(float4) * F * N, stream_));
-        cs.batchSummedCap = F * N;
-    }
-    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.entryCap < F * N) {   // keep the allocations out of the timed region
-        dfree(cs.dEntries);
-        cs.dEntries = dallocT<int4>(F * N);
-        cs.entryCap = F * N;
-        cs.entriesValid = false;
-    }
-    if (entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)) &&
-        cs.listCap < F * N) {
-        dfree(cs.dLists);
-        cs.dLists = dallocT<int>(F * N * static_cast<size_t>(candidateListStride()));
-        cs.listCap = F * N;
-        cs.entriesValid = false;
-    }
-    if (wavefront && entryFrontierActive(cs, static_cast<int>(F)) && cs.S % 32 == 0 && (candidateLists >= 2 || (candidateLists == 1 && F >= 4)))
-        ensureQueue(cs, F);
+    ensureBatchBuffers(cs, F, fused);                    // (allocations stay out of the timed region)
     if (cs.batchPoseCap < count) {
         dfree(cs.dBatchPoses);
         cs.dBatchPoses = dallocT<DevicePose>(count);
@@ -907,6 +1067,8 @@ void Renderer::debugCopyRngStates(uint32_t* out8)
     if (!compoundActive()) return;
     CompoundState& cs = compoundState(current_);
     if (!cs.dRng) return;
+    dropReadAhead(cs);                                   // the states the CALLER has reached, not those of frames rendered ahead
+    if (cs.needRewind) prepareCompound(cs, camera());
     const size_t N = static_cast<size_t>(cs.rngN), S = static_cast<size_t>(cs.rngS);
     std::vector<uint32_t> tmp(8 * N * S);
     CR_CUDA(cudaMemcpyAsync(tmp.data(), cs.dRng, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, stream_));

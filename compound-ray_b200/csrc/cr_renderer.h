@@ -45,6 +45,18 @@ struct CompoundState {                 // device side of one CompoundEye camera
     bool lastPoseValid = false; DevicePose lastPose{}; uint64_t lastPoseEyeVersion = 0; int standingFrames = 0;   // consecutive single frames from one pose
     DevicePose entriesPose{};                                                               // a single frame of this eye at this pose
     float4* dPartials = nullptr; size_t partialCap = 0;   // fused reduction: [frames][N][S/32] warp partials
+    // Read-ahead for a standing camera (renderFrame): frames [next, count) of one batched launch wait to be handed out; the sample
+    // streams on the device are (count - next) frames ahead of frameIndex.  Dropping them rewinds the streams (needRewind).
+    struct ReadAhead {
+        int count = 0, next = 0, rowPixels = 0, S = 0, N = 0;
+        DevicePose pose{};
+        uint64_t eyeVersion = 0;
+        bool fused = false, fast = false;
+        double traceMsPerFrame = 0.0;
+    } ahead;
+    bool needRewind = false; uint64_t rewindTo = 0;
+    uchar4* dAheadRows = nullptr; unsigned char* hAheadRows = nullptr; size_t aheadRowCap = 0;   // [frames][N] 8-bit rows, device + pinned host
+    double lastSingleFrameMs = 0.0;                      // host time of the last frame rendered on its own
     // wavefront queue (k_traceCompound -> k_traceQueue -> k_shadeQueue): rays of the warp-frames without a candidate list
     float4* dQueueRays = nullptr; int4* dQueueHits = nullptr; int* dQueueWarps = nullptr; unsigned* dQueueCounters = nullptr; size_t queueCap = 0;
     // debug dump buffers
@@ -92,6 +104,13 @@ public:
     // that build candidate lists, queueFraction = share of a launch's rays the queue is sized for
     // (a warp that finds it full walks inline), wavefrontRefill = lanes below which k_traceQueue fetches new rays.
     bool zeroCopyFrames = true;        // single_dimension_fast rows written straight into the pinned host frame (no D2H copy queued)
+    // Standing camera: once three consecutive renderFrame calls found the same pose, eye and sample count, the following frames
+    // (single_dimension_fast, small enough) are rendered several at a time in ONE batched launch -- the streams simply run
+    // ahead -- and handed out one per call; any change drops what is left and rewinds the streams (k_rngInit at the frame
+    // index actually consumed).  readAheadBudgetMs bounds the GPU time of one such launch, readAheadMaxRays the frame size.
+    bool readAhead = true;
+    double readAheadBudgetMs = 1.5;
+    long long readAheadMaxRays = 2ll << 20;
     bool standingFrontier = true;      // small frames: build the frontier once the camera has stood still for three frames, then reuse it
     bool spinSync = false;             // cudaDeviceScheduleSpin (CR_SPIN_SYNC=1, before the first GPU use)
     int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)
@@ -150,9 +169,16 @@ private:
     void launchCompound(CompoundState& cs, const HostCamera& cam, const Pose& pose, uchar4* fastRow = nullptr, int fastRowCount = 0,
                         uchar4* fastRowHost = nullptr);
     void launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, int nFrames, float* dSamples, float4* dSummed,
-                             uchar4* fastRow = nullptr);
+                             uchar4* fastRow = nullptr, const Pose* samePose = nullptr);
     bool fusedActive(const CompoundState& cs, const HostCamera& cam) const;
     void ensurePartials(CompoundState& cs, size_t frames);
+    void ensureBatchBuffers(CompoundState& cs, size_t F, bool fused);
+    size_t batchFramesPerLaunch(const CompoundState& cs, size_t count, bool fused) const;
+    void noteSinglePose(CompoundState& cs, const DevicePose& pose);
+    bool consumeReadAhead(CompoundState& cs, const HostCamera& cam, bool eligible);
+    bool launchReadAhead(CompoundState& cs, const HostCamera& cam);
+    void dropReadAhead(CompoundState& cs);
+    bool readAheadEligible(const CompoundState& cs, const HostCamera& cam) const;
     void ensureQueue(CompoundState& cs, size_t frames);
     size_t queueRaysFor(const CompoundState& cs, size_t frames) const;
     void attachQueue(CompoundState& cs, EyeParams& ep);

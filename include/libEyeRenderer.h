@@ -217,6 +217,13 @@ void crDebugSetWavefront(int on, int refillBelow, double queueFraction);
  * leaves as soon as fewer than `lanes` (1..32) lanes still want a node; 1 = classic while-while (a lane at a leaf waits
  * for every other lane).  Each lane's own sequence of node and triangle tests does not change: same hits. */
 void crDebugSetNodeLanes(int lanes);
+/* Read-ahead for a standing camera (default on): once three consecutive renderFrame calls found the same pose, eye and
+ * sample count, the following single_dimension_fast frames of up to 2M rays are rendered several at a time in one
+ * batched launch of at most `budgetMs` (default 1.5; <= 0 keeps it) and handed out one per call; anything that changes
+ * (pose, eye, samples, mode, size, a batch call, crSetFirstFrame ...) drops what is left and rewinds the sample streams to
+ * the frame the caller has reached.  The frames are those of one-at-a-time rendering bit for bit; renderFrame's return
+ * value is the time THAT call took (the launching call carries the batch). */
+void crDebugSetReadAhead(int on, double budgetMs);
 /* Device-side breakdown of renderFrame for a compound eye: with the profile on, event marks are recorded inside the frame
  * and crDebugFrameBreakdown returns the milliseconds of [frontier pass (+ counter reset), trace kernel(s), reduction kernel]
  * of the last frame (-1 when there is none). */

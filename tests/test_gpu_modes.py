@@ -37,6 +37,7 @@ def _default_modes(lib):
     lib.crDebugSetWavefront(0, 24, 0.35)
     lib.crDebugSetNodeLanes(16)
     lib.crDebugSetDynamicChunks(1)
+    lib.crDebugSetReadAhead(1, 1.5)
     lib.crDebugSetRayDump(False)
     lib.crDebugSetEntryFrontier(1, 2, 0)
     lib.crSetFirstFrame(0)
@@ -222,6 +223,72 @@ def test_wavefront_queue_changes_no_bit(lib, er, loader, oracle, terrain):
                 assert np.array_equal(a, b), (fused, key)
         assert np.array_equal(out[(fused, "off")][1][0], out[(fused, "off")][2][0])
     lib.crSetRenderMode(0, 0)
+
+
+def test_read_ahead_for_a_standing_camera_changes_no_byte(lib, er, ref_data):
+    """renderFrame from a standing camera renders several frames per launch and hands them out one per call.  A script of
+    calls -- long standing runs, a move in the middle of a run, setOmmatidia with the same count (streams persist),
+    setCurrentEyeSamplesPerOmmatidium with the same S (streams restart), a pose batch in between, a mode switch, reading
+    the stream states -- gives the same rows, float RGB and XORWOW states with the read-ahead on as with it off."""
+    path = os.path.join(ref_data, "data", "natural-standin-sky.gltf")
+    lib.loadGlTFscene(path.encode())
+    er.gotoFirstCompoundEye(lib)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    eye = er.readEyeFile(os.path.join(ref_data, "data", "eyes", "1000-equidistant.eye"))
+    er.setOmmatidiaFromOmmatidiumList(lib, eye)
+    N = lib.getCurrentEyeOmmatidialCount()
+    er.setRenderSize(lib, N, 1)
+    pose0 = np.zeros(12, np.float32); lib.crDebugCopyCameraPose(pose0.ctypes.data)
+
+    def script(read_ahead):
+        lib.crDebugSetReadAhead(read_ahead, 1.5)
+        lib.crSetRenderMode(0, 0)
+        lib.setCameraPosition(*[float(v) for v in pose0[:3]])
+        lib.setCurrentEyeSamplesPerOmmatidium(32)
+        out, launches = [], []
+
+        def frames(n):
+            for _ in range(n):
+                l0 = lib.crGetLaunchCount()
+                lib.renderFrame()
+                launches.append(lib.crGetLaunchCount() - l0)
+                out.append(er.getFrame(lib, N, 1).copy())
+                out.append(er.getOmmatidialData(lib).copy())
+
+        def states():
+            st = np.zeros((N * lib.getCurrentEyeSamplesPerOmmatidium(), 8), np.uint32)
+            lib.crDebugCopyRngStates(st.ctypes.data)
+            st[:, 7] = np.where(st[:, 6] == 1, st[:, 7], 0)   # the cached Box-Muller half is dead while its flag is clear
+            out.append(st)                                    # (a rewound stream holds 0 there, a run-through stream the stale value)
+
+        frames(45)                                           # long standing run: several read-ahead launches
+        states()                                             # ... in the middle of one: the states the caller has reached
+        frames(5)
+        lib.setCameraPosition(float(pose0[0]), float(pose0[1]) + 0.5, float(pose0[2]))   # move inside a read-ahead run
+        frames(9)
+        lib.setCurrentEyeSamplesPerOmmatidium(32)            # same S: the streams restart at frame 0
+        frames(12)
+        er.setOmmatidiaFromOmmatidiumList(lib, eye[::-1])    # same count, other table: the streams persist
+        frames(8)
+        er.setOmmatidiaFromOmmatidiumList(lib, eye)
+        rows, _ = er.renderPoseBatch(lib, np.tile(pose0, (3, 1)))      # a batch in between continues where the caller is
+        out.append(rows.copy())
+        frames(7)
+        lib.crSetRenderMode(1, 0)                            # fused reduction from here on, streams persist
+        frames(11)
+        lib.setCurrentEyeSamplesPerOmmatidium(64)
+        frames(6)
+        states()
+        lib.crSetRenderMode(0, 0)
+        return out, launches
+
+    off, l_off = script(0)
+    on, l_on = script(1)
+    assert len(off) == len(on)
+    for k, (a, b) in enumerate(zip(off, on)):
+        assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"output {k} differs with the read-ahead on"
+    assert sum(1 for v in l_on if v == 0) > len(l_on) // 2, "most frames should have been handed out without a launch"
+    assert all(v > 0 for v in l_off)
 
 
 def test_fused_reduction_fixed_order_and_tolerance(lib, er, loader, oracle, terrain):
