@@ -151,20 +151,17 @@ def poses_for(cam_pos, axes, count, first_index):
 
 def traversal_counters(lib, er, S_probe=32):
     """Per-ray BVH nodes fetched / triangles tested, counted ON THE DEVICE by the dump variant of the trace
-    kernel (same code path: entry frontier and candidate lists included -- a listed ray counts every element of its
-    ommatidium's list as a node fetch) on a probe frame of S_probe samples, plus the same figures for a plain root-to-leaf walk counted by
+    kernel (same code path, entry frontier included) on a probe frame of S_probe samples, plus the same figures for a plain root-to-leaf walk counted by
     the CPU oracle's instrumented traversal of the IDENTICAL device BVH on the product's own rays (which also
     re-checks the hit ids)."""
     from oracle import oracle as O
     N = lib.getCurrentEyeOmmatidialCount()
     S_keep = lib.getCurrentEyeSamplesPerOmmatidium()
     lib.setCurrentEyeSamplesPerOmmatidium(S_probe)
-    lib.crDebugSetEntryFrontier(1, -1, 0)            # the probe frame is small and single: keep the frontier pass and the
-    lib.crDebugSetCandidateLists(2)                  # candidate lists of the timed (batched) frames
+    lib.crDebugSetEntryFrontier(1, -1, 0)            # the probe frame is small and single: keep the frontier pass of the timed frames
     lib.crDebugSetRayDump(True)
     lib.renderFrame()
     lib.crDebugSetEntryFrontier(1, -1, 3 << 18)
-    lib.crDebugSetCandidateLists(1)
     n = N * S_probe
     o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); h = np.zeros((n, 4), np.int32)
     lib.crDebugCopyLastRays(o.ctypes.data, d.ctypes.data, h.ctypes.data)

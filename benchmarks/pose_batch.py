@@ -68,11 +68,11 @@ def main():
     all_poses = er.make_poses(pos, x=pose[3:6], y=pose[6:9], z=pose[9:12])
     poses = all_poses[lo:hi]
     lib.crSetFirstFrame(lo)
-    er.renderPoseBatch(lib, poses[:min(8, len(poses))])                      # warm-up (then rewind the streams)
+    er.renderPoseBatch(lib, poses[:min(2048, len(poses))])                   # warm-up: allocations, module load, clocks (then rewind the streams)
     lib.crSetFirstFrame(lo)
     if args.native:
         sharding.init_library_comm(lib, rank, world, dist if use_torch else None, args.id_file)
-        sharding.render_pose_batch_sharded(lib, all_poses[:min(8 * world, P)], chunk=args.chunk)      # warm-up incl. the collective
+        sharding.render_pose_batch_sharded(lib, all_poses[:min(1024 * world, P)], chunk=args.chunk)   # warm-up incl. the collective
         dev_out = None
         try:                                        # result stays in device memory on every rank, as in the torch legs below
             import torch

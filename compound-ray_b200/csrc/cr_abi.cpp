@@ -378,6 +378,7 @@ void crDebugSetWavefront(int on, int refillBelow, double queueFraction)
     if (queueFraction >= 0.0) renderer().queueFraction = queueFraction;
 }
 void crDebugSetNodeLanes(int lanes) { renderer().nodeLanes = lanes; }
+void crDebugSetFrameGroups(int on) { renderer().frameGroups = on != 0; }
 void crDebugSetReadAhead(int on, double budgetMs)
 {
     renderer().readAhead = on != 0;

@@ -68,6 +68,9 @@ struct alignas(16) DevicePose {
 struct EyeParams {
     const float4* pre = nullptr;  // kPreStride float4 per ommatidium (k_prepOmmatidia)
     uint4* rng = nullptr;
+    uint4* rngOut = nullptr;      // batches: where the states go after the launch (= rng unless the launch is cut into frame groups)
+    int frameGroups = 1;          // batches of small frames: the launch's frames in this many groups of groupFrames (even) frames,
+    int groupFrames = 0;          // a work unit = (32 rays, one group); needs the launch to start at an even frame
     float4* summed = nullptr;
     float* samples = nullptr;     // [o][s][3] per-sample colour/S
     // optional per-ray dump (debug / parity): reference stream-id order [N*s+o]

@@ -949,7 +949,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
 // Traversal: warps whose 32 lanes are samples of one ommatidium with a candidate list (k_buildEntries, stage 2) test
 // that list (traceList); everything else walks the BVH per lane from the entry frontier or the root (traceClosest).
 // ------------------------------------------------------------------------------------------
-template <bool DUMP, bool MULTI, bool FUSED, bool FAST>
+template <bool DUMP, bool MULTI, bool FUSED, bool FAST, bool GROUPED = false>
 __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCompound(const DeviceScene sc, const EyeParams ep)
 {
     __shared__ int sStack[kSmemStack][kTraceThreads];
@@ -967,7 +967,14 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     // ones from a global counter (one atomic per chunk, issued a whole chunk before its answer is needed).  With the static grid-stride split the warps finished up to 15 % apart (sky, listed, walking and queued units
     // cost between 1x and 6x; sm__warps_active 41.8 of 50 %, profiles/r02j_k1_queue_ncu_summary.txt).
     const unsigned gridWarps = gridDim.x * (kTraceThreads / 32u);
-    const unsigned nUnits = (total + 31u) >> 5;
+    // Small frames (batches): the launch's F frames are cut into G groups of groupFrames (an EVEN number of) frames and a unit
+    // is (32 rays, one group) -- G times as many units for the counter to balance.  The streams of a group start where the
+    // previous group leaves them: its lanes load the launch's starting state and step it over the draws of the frames before
+    // their group (2 draws per frame on average: 3 + 1 per frame pair, the Box-Muller cache empty at every even frame --
+    // the renderer only splits launches that start at an even frame).  Only the last group writes states, to rngOut.
+    const unsigned rayUnits = (total + 31u) >> 5;
+    const unsigned groups = (MULTI && GROUPED) ? (unsigned)max(1, ep.frameGroups) : 1u;
+    const unsigned nUnits = rayUnits * groups;
     const unsigned chunkUnits = MULTI ? 1u : (unsigned)max(1, ep.chunkUnits);
     const unsigned nChunks = (nUnits + chunkUnits - 1u) / chunkUnits;
     // Two chunks are known ahead (the first two of every warp by its position in the grid): while chunk i is traced, the
@@ -977,14 +984,15 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     while (chunk < nChunks) {                                              // (warp-uniform)
       unsigned afterNext = nextChunk + gridWarps;                           // static split when there is no counter
       if (ep.workCounter != nullptr && lane == 0) afterNext = atomicAdd(ep.workCounter, 1u) + 2u * gridWarps;
-      {
+      if (groups == 1u) {
           const size_t rn = ((size_t)nextChunk * chunkUnits << 5) + (unsigned)lane;
           if (rn < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * rn));
       }
       for (unsigned k = 0; k < chunkUnits; k++) {
         const unsigned unit = chunk * chunkUnits + k;
         if (unit >= nUnits) break;                                          // (warp-uniform)
-        const unsigned r0 = (unit << 5) + (unsigned)lane;
+        const unsigned group = (GROUPED && groups > 1u) ? unit / rayUnits : 0u;   // group-major: every ray unit of group 0 first
+        const unsigned r0 = ((unit - group * rayUnits) << 5) + (unsigned)lane;
 #if CR_INLINE_PHASED
         // a warp stays whole (the phased traversal votes across its lanes): the lanes of the last warp beyond the last
         // ray (N*S % 32 != 0) redo ray total-1 and store nothing
@@ -1006,9 +1014,14 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
 #else
         Rng rng = rngLoad(statePtr);
 #endif
+        const int fBegin = (MULTI && GROUPED) ? (int)group * ep.groupFrames : 0;
+        const int fEnd = (MULTI && GROUPED) ? min(F, fBegin + (groups > 1u ? ep.groupFrames : F)) : F;
+        if (MULTI && GROUPED && group > 0u) {                      // the draws of the frames before this group
+            for (int i = 2 * fBegin; i > 0; i--) (void)rngNext(rng);
+        }
         // Consecutive frames of one sample stream are processed back to back by the same lane: the
         // state is loaded and stored once per batch, and one launch covers F frames (poses).
-        for (int f = 0; f < F; f++) {
+        for (int f = fBegin; f < fEnd; f++) {
             DevicePose pose = ep.pose;
             if (MULTI) {
                 const float4* pp = reinterpret_cast<const float4*>(ep.poses + f);
@@ -1115,7 +1128,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                 if (ep.dumpCounts) ep.dumpCounts[id] = make_int2(nNode, nTri);   // nodes fetched / triangles tested by THIS kernel
             }
         }
-        if (MULTI && valid) rngStore(statePtr, rng);
+        if (MULTI && valid && (!GROUPED || group + 1u == groups)) rngStore(ep.rngOut + 2 * (size_t)r, rng);
 #if !CR_INLINE_PHASED
         }
 #endif
@@ -1252,42 +1265,51 @@ __global__ void __launch_bounds__(128) k_shadeQueue(const DeviceScene sc, const 
 // K1b of the fused mode: summed[f][o] = fixed-order sum of the S/32 warp partials of the row, one warp per row.
 // Lane l first adds partials l, l+32, l+64, ... in ascending order, then the same butterfly as in K1 combines the 32
 // lanes (S <= 1024: one partial per lane).  Also writes the 8-bit row of single_dimension_fast / pose batches.
-constexpr int kSumPartialRows = 32;          // rows (warps) per CTA of k_sumPartials: its 32 pixels leave as ONE 128-byte store
+// Rows with few partials (S <= 512) share a warp: a row takes W = the power of two >= S/32 lanes, 32/W rows per warp.
+// The value is that of the one-warp-per-row form bit for bit: there the lanes beyond S/32 hold +0.0f, so the butterfly
+// levels d >= W only add zeros (x + 0.0f = x: the partial sums of colours are never -0.0f) and the levels d < W pair the
+// same lanes in the same order as the sub-warp butterfly here.  (S = 64: 16 rows per warp; one warp per row spent
+// 0.73 ms per 256-frame launch of the 6 374-ommatidia eye on two partials per row, profiles/r02v_cfg5_metrics.csv.)
+constexpr int kSumPartialWarps = 32;         // warps per CTA of k_sumPartials
 template <bool FAST>
-__global__ void __launch_bounds__(32 * kSumPartialRows) k_sumPartials(const float4* __restrict__ partials, int NF, int blocksPerRow,
-                                                                      float4* __restrict__ summed, uchar4* __restrict__ fastRow,
-                                                                      int fastRowCount, uchar4* __restrict__ fastRowHost)
+__global__ void __launch_bounds__(32 * kSumPartialWarps) k_sumPartials(const float4* __restrict__ partials, int NF, int blocksPerRow,
+                                                                       int lanesPerRow, float4* __restrict__ summed,
+                                                                       uchar4* __restrict__ fastRow, int fastRowCount,
+                                                                       uchar4* __restrict__ fastRowHost)
 {
-    __shared__ uchar4 sPx[kSumPartialRows];
+    __shared__ uchar4 sPx[32 * kSumPartialWarps];
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
-    const int row0 = (int)blockIdx.x * kSumPartialRows, row = row0 + warp;
-    if (row < NF) {                                          // warp-uniform
+    const int rowsPerWarp = 32 / lanesPerRow, rowsPerCta = rowsPerWarp * kSumPartialWarps;
+    const int row0 = (int)blockIdx.x * rowsPerCta;
+    const int sub = lane / lanesPerRow, l = lane - sub * lanesPerRow;      // my row within the warp, my lane within the row
+    const int rowInCta = warp * rowsPerWarp + sub, row = row0 + rowInCta;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    if (row < NF) {
         const float4* p = partials + (size_t)row * blocksPerRow;
-        float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-        for (int k = lane; k < blocksPerRow; k += 32) {
+        for (int k = l; k < blocksPerRow; k += lanesPerRow) {               // (lanesPerRow == 32 whenever blocksPerRow > 32)
             const float4 q = __ldcs(p + k);
             cx += q.x; cy += q.y; cz += q.z;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            cx += __shfl_xor_sync(kFullMask, cx, d);
-            cy += __shfl_xor_sync(kFullMask, cy, d);
-            cz += __shfl_xor_sync(kFullMask, cz, d);
-        }
-        if (lane == 0) {
-            summed[row] = make_float4(cx, cy, cz, 0.0f);
-            if (fastRow != nullptr) sPx[warp] = makeColor<FAST>(cx, cy, cz);
-        }
+    }
+    for (int d = lanesPerRow >> 1; d > 0; d >>= 1) {                        // (all 32 lanes take part: uniform trip count)
+        cx += __shfl_xor_sync(kFullMask, cx, d);
+        cy += __shfl_xor_sync(kFullMask, cy, d);
+        cz += __shfl_xor_sync(kFullMask, cz, d);
+    }
+    if (row < NF && l == 0) {
+        summed[row] = make_float4(cx, cy, cz, 0.0f);
+        if (fastRow != nullptr) sPx[rowInCta] = makeColor<FAST>(cx, cy, cz);
     }
     if (fastRow == nullptr) return;                          // (uniform)
     __syncthreads();
-    // the CTA's 32 pixels as one coalesced 128-byte store -- to the device frame and, when the caller reads every frame,
-    // straight into the pinned (mapped) host frame: 313 PCIe writes of 128 bytes per 10 000-ommatidia row instead of a
-    // copy queued behind the kernel (or 10 000 writes of 4 bytes: 22 us)
-    if (warp == 0 && row0 + lane < NF && row0 + lane < fastRowCount) {
-        const uchar4 px = sPx[lane];
-        fastRow[row0 + lane] = px;
-        if (fastRowHost != nullptr) fastRowHost[row0 + lane] = px;
+    // the CTA's pixels as coalesced stores -- to the device frame and, when the caller reads every frame, straight into the
+    // pinned (mapped) host frame: 128-byte PCIe writes instead of a copy queued behind the kernel (or 10 000 writes of
+    // 4 bytes: 22 us)
+    const int t = (int)threadIdx.x;
+    if (t < rowsPerCta && row0 + t < NF && row0 + t < fastRowCount) {
+        const uchar4 px = sPx[t];
+        fastRow[row0 + t] = px;
+        if (fastRowHost != nullptr) fastRowHost[row0 + t] = px;
     }
 }
 
@@ -1660,7 +1682,8 @@ void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t str
 template <bool FUSED, bool FAST>
 static void launchTraceT(const DeviceScene& sc, const EyeParams& eye, int grid, cudaStream_t stream)
 {
-    if (eye.poses) k_traceCompound<false, true, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    if (eye.poses && eye.frameGroups > 1) k_traceCompound<false, true, FUSED, FAST, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
+    else if (eye.poses) k_traceCompound<false, true, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false, false, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
 }
 
@@ -1669,8 +1692,12 @@ static void launchSumT(const EyeParams& eye, cudaStream_t stream)
 {
     const long long nf = (long long)eye.N * eye.nFrames;
     if (eye.fused) {
-        k_sumPartials<FAST><<<(unsigned)((nf + kSumPartialRows - 1) / kSumPartialRows), 32 * kSumPartialRows, 0, stream>>>(eye.partials, (int)nf, eye.S >> 5, eye.summed, eye.fastRow,
-                                                                                  eye.fastRowCount, eye.fastRowHost);
+        const int bpr = eye.S >> 5;
+        int lanesPerRow = 1;
+        while (lanesPerRow < bpr && lanesPerRow < 32) lanesPerRow <<= 1;
+        const long long rowsPerCta = (32 / lanesPerRow) * (long long)kSumPartialWarps;
+        k_sumPartials<FAST><<<(unsigned)((nf + rowsPerCta - 1) / rowsPerCta), 32 * kSumPartialWarps, 0, stream>>>(
+            eye.partials, (int)nf, bpr, lanesPerRow, eye.summed, eye.fastRow, eye.fastRowCount, eye.fastRowHost);
         return;
     }
     static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();

@@ -68,6 +68,7 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
     if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
+    if (const char* e = getenv("CR_FRAME_GROUPS")) frameGroups = atoi(e) != 0;
     if (const char* e = getenv("CR_READ_AHEAD")) readAhead = atoi(e) != 0;
     if (const char* e = getenv("CR_READ_AHEAD_MS")) readAheadBudgetMs = atof(e);
     if (const char* e = getenv("CR_SPIN_SYNC")) spinSync = atoi(e) != 0;
@@ -133,7 +134,8 @@ DevicePose Renderer::toDevicePose(const Pose& p)
 // ------------------------------------------------------------------------------------------
 void Renderer::freeCompound(CompoundState& cs)
 {
-    dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
+    dfree(cs.dOmm); dfree(cs.dPre); dfree(cs.dRng); dfree(cs.dRngAlt); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dMap);
+    cs.rngAltCap = 0;
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
     dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries); dfree(cs.dPartials); dfree(cs.dLists);
     dfree(cs.dQueueRays); dfree(cs.dQueueHits); dfree(cs.dQueueWarps); dfree(cs.dQueueCounters);
@@ -400,7 +402,8 @@ void Renderer::prepareCompound(CompoundState& cs, HostCamera& cam)
         cs.ommDirty = false;
     }
     if (cs.rngN != N || cs.rngS != cs.S || !cs.dRng) {
-        dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples);
+        dfree(cs.dRng); dfree(cs.dSummed); dfree(cs.dSamples); dfree(cs.dRngAlt);
+        cs.rngAltCap = 0;
         cs.dLastSummed = nullptr;
         cs.dRng = dallocT<uint4>(2 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
         cs.dSamples = dallocT<float>(3 * static_cast<size_t>(N) * static_cast<size_t>(cs.S));
@@ -646,11 +649,37 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     ep.fastRowCount = fastRow ? cs.N * nFrames : 0;
     ep.pre = cs.dPre;
     ep.rng = cs.dRng;
+    ep.rngOut = cs.dRng;
     ep.summed = dSummed;
     ep.samples = dSamples;
     ep.N = cs.N;
     ep.S = cs.S;
     ep.nFrames = nFrames;
+    // Small frames: too few units of 32 rays for the work counter to balance (the 6 374 x 64 eye of the toy experiment: 2.7 per
+    // warp, sm__warps_active 40 of 50 %; a 1000 x 1 eye: 32 units for 4 736 warps).  Cut the launch's frames into groups
+    // (EyeParams::frameGroups) -- possible when the launch starts at an even frame, where no stream holds a cached normal.
+    bool grouped = false;
+    if (frameGroups && nFrames >= 4 && (cs.frameIndex & 1ull) == 0 && !dumpRays) {
+        const long long rayUnits = (static_cast<long long>(cs.N) * cs.S + 31) / 32;
+        const long long wantUnits = 8ll * numSMs_ * traceOcc_ * (kTraceThreads / 32);
+        long long G = std::min<long long>((wantUnits + rayUnits - 1) / std::max<long long>(1, rayUnits), nFrames / 2);
+        if (G > 1) {
+            const int Fg = 2 * static_cast<int>((nFrames + 2 * G - 1) / (2 * G));
+            G = (nFrames + Fg - 1) / Fg;
+            if (G > 1) {
+                const size_t words = 2 * static_cast<size_t>(cs.N) * static_cast<size_t>(cs.S);
+                if (cs.rngAltCap < words) {
+                    dfree(cs.dRngAlt);
+                    cs.dRngAlt = dallocT<uint4>(words);
+                    cs.rngAltCap = words;
+                }
+                ep.frameGroups = static_cast<int>(G);
+                ep.groupFrames = Fg;
+                ep.rngOut = cs.dRngAlt;
+                grouped = true;
+            }
+        }
+    }
     if (samePose) {                         // every frame of the launch from one pose (read-ahead): ONE frontier row serves them all
         ep.pose = toDevicePose(*samePose);
         ep.nFrames = 1;
@@ -672,6 +701,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
     const long long slots = static_cast<long long>(numSMs_) * traceOcc_;
     launchTraceCompound(dscene_, ep, static_cast<int>(slots), stream_);
     launches_ += 2;
+    if (grouped) std::swap(cs.dRng, cs.dRngAlt);         // the last group wrote the states there
     cs.frameIndex += static_cast<uint64_t>(nFrames);
     cs.dLastSummed = dSummed + static_cast<size_t>(nFrames - 1) * static_cast<size_t>(cs.N);
 }

@@ -30,6 +30,7 @@ struct CompoundState {                 // device side of one CompoundEye camera
     uint64_t mapEyeVersion = 0, eyeVersion = 1;
     int N = 0, S = 1;
     int rngN = 0, rngS = 0;            // allocation the RNG/summed buffers were sized for
+    uint4* dRngAlt = nullptr; size_t rngAltCap = 0;   // second state array: launches cut into frame groups write the final states there (then swapped)
     bool ommDirty = true;
     bool randomsConfigured = false;    // cameras/CompoundEyeDataTypes.h:12
     uint64_t frameIndex = 0;           // frames rendered since the streams were (re)initialised
@@ -98,7 +99,10 @@ public:
     // Default: ordered sum + cr_math.h = every output bit equal to the CPU checker.
     bool fusedReduce = false;          // K1 sums 32 samples per warp in-kernel (fixed order, RGB equal to rounding) -- no sample buffer
     bool fastMath = false;             // hardware sin/cos/log/pow, as the reference's --use_fast_math build
-    int candidateLists = 1;            // per-ommatidium candidate lists: 0 never, 1 in batches of >= 4 frames (default), 2 always
+    int candidateLists = 0;            // per-ommatidium candidate lists: 0 never (default), 1 in batches of >= 4 frames, 2 always.  They paid
+                                       // +1.7 % while the trace kernel split its work statically; with units from the work counter they
+                                       // are +-0 on the headline workload and -7 % on the 6 374 x 64 pose batches (their pass costs more
+                                       // than the lockstep test saves): profiles/r02x_small_batch_ab.json
     // Wavefront queue for the warp-frames that have no candidate list (they need the lists: same launches): 0 never
     // (default since the trace kernel hands its units out dynamically: 23.2 vs 22.3 Grays/s with the queue), 1 in launches
     // that build candidate lists, queueFraction = share of a launch's rays the queue is sized for
@@ -108,6 +112,7 @@ public:
     // (single_dimension_fast, small enough) are rendered several at a time in ONE batched launch -- the streams simply run
     // ahead -- and handed out one per call; any change drops what is left and rewinds the streams (k_rngInit at the frame
     // index actually consumed).  readAheadBudgetMs bounds the GPU time of one such launch, readAheadMaxRays the frame size.
+    bool frameGroups = true;           // batched launches of small frames: units of (32 rays, a group of frames) instead of (32 rays, all frames)
     bool readAhead = true;
     double readAheadBudgetMs = 1.5;
     long long readAheadMaxRays = 2ll << 20;

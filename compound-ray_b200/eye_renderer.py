@@ -117,6 +117,7 @@ def configureFunctions(eyeRenderer):
     r.crDebugSetCandidateLists.argtypes = [C.c_int]
     r.crDebugSetWavefront.argtypes = [C.c_int, C.c_int, C.c_double]
     r.crDebugSetNodeLanes.argtypes = [C.c_int]
+    r.crDebugSetFrameGroups.argtypes = [C.c_int]
     r.crDebugSetReadAhead.argtypes = [C.c_int, C.c_double]
     r.crDebugSetFrameProfile.argtypes = [C.c_int]
     r.crDebugFrameBreakdown.argtypes = [vp]

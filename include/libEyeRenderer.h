@@ -197,9 +197,10 @@ void crDebugSetRayDump(bool on);
 void crDebugSetEntryFrontier(int on, int minSamples, long long minRaysPerFrame);
 /* Switch of the per-ommatidium candidate lists (they need the entry frontier and S % 32 == 0): the frontier pass also
  * flattens what an ommatidium's sample cone can reach into a list of <= 15 pre-leaf BVH nodes, which the 32 samples a warp
- * holds of that ommatidium test in lockstep instead of walking the tree per lane.  0 = never, 1 = in launches that cover
- * at least 4 frames (default: the extra latency of building them hides behind a batch, not behind one synchronous frame),
- * 2 = always.  The closest hit is the same either way. */
+ * holds of that ommatidium test in lockstep instead of walking the tree per lane.  0 = never (default since round 2: with the
+ * trace kernel's dynamic work distribution they no longer pay), 1 = in launches that cover at least 4 frames (the extra
+ * latency of building them hides behind a batch, not behind one synchronous frame), 2 = always.  The closest hit is the
+ * same either way. */
 void crDebugSetCandidateLists(int on);
 /* The candidate lists of the last trace launch: 16 ints per (frame, ommatidium) -- [0] = element count (-1: none, the
  * frontier is walked per lane; 0: the cone reaches no leaf), [1..] = node << 2 | reachable-leaf mask.  Returns the
@@ -217,6 +218,10 @@ void crDebugSetWavefront(int on, int refillBelow, double queueFraction);
  * leaves as soon as fewer than `lanes` (1..32) lanes still want a node; 1 = classic while-while (a lane at a leaf waits
  * for every other lane).  Each lane's own sequence of node and triangle tests does not change: same hits. */
 void crDebugSetNodeLanes(int lanes);
+/* Batched launches of small frames (default on): when a launch has too few units of 32 rays for the trace kernel's work
+ * counter to balance, its frames are cut into groups and a unit becomes (32 rays, one group of frames); the lanes of a later
+ * group step the launch's starting stream states over the draws of the frames before it.  Same frames bit for bit. */
+void crDebugSetFrameGroups(int on);
 /* Read-ahead for a standing camera (default on): once three consecutive renderFrame calls found the same pose, eye and
  * sample count, the following single_dimension_fast frames of up to 2M rays are rendered several at a time in one
  * batched launch of at most `budgetMs` (default 1.5; <= 0 keeps it) and handed out one per call; anything that changes

@@ -38,6 +38,7 @@ def _default_modes(lib):
     lib.crDebugSetNodeLanes(16)
     lib.crDebugSetDynamicChunks(1)
     lib.crDebugSetReadAhead(1, 1.5)
+    lib.crDebugSetFrameGroups(1)
     lib.crDebugSetRayDump(False)
     lib.crDebugSetEntryFrontier(1, 2, 0)
     lib.crSetFirstFrame(0)
@@ -222,6 +223,53 @@ def test_wavefront_queue_changes_no_bit(lib, er, loader, oracle, terrain):
             for a, b in zip(out[(fused, "off")], out[(fused, key)]):
                 assert np.array_equal(a, b), (fused, key)
         assert np.array_equal(out[(fused, "off")][1][0], out[(fused, "off")][2][0])
+    lib.crSetRenderMode(0, 0)
+
+
+def test_frame_groups_in_small_batches_change_no_byte(lib, er, ref_data):
+    """Batched launches of small frames cut their frames into groups (a work unit = 32 rays x one group; later groups step
+    the stream states over the frames before them).  Batches that start at even and at odd frames, of lengths that do and
+    do not divide into the groups, in both reductions: rows, float RGB of the last frame and the stream states afterwards
+    equal the ungrouped launches and the frame-by-frame loop."""
+    path = os.path.join(ref_data, "data", "natural-standin-sky.gltf")
+    lib.loadGlTFscene(path.encode())
+    er.gotoFirstCompoundEye(lib)
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    N = lib.getCurrentEyeOmmatidialCount()
+    er.setRenderSize(lib, N, 1)
+    lib.crDebugSetReadAhead(0, 0.0)
+    pose0 = np.zeros(12, np.float32); lib.crDebugCopyCameraPose(pose0.ctypes.data)
+    rng = np.random.default_rng(3)
+    lengths = [9, 7, 8, 33, 4, 5]                               # starts at frames 0, 9 (odd: not grouped), 16, 24, 57 (odd), 61 (odd)
+    poses = [np.tile(pose0, (n, 1)) for n in lengths]
+    for p in poses:
+        p[:, :3] += rng.uniform(-0.5, 0.5, size=(len(p), 3)).astype(np.float32)
+
+    def states(S):
+        st = np.zeros((N * S, 8), np.uint32)
+        lib.crDebugCopyRngStates(st.ctypes.data)
+        st[:, 7] = np.where(st[:, 6] == 1, st[:, 7], 0)
+        return st
+
+    for fused, S in ((0, 40), (1, 32)):
+        out = {}
+        for groups in (0, 1):
+            lib.crDebugSetFrameGroups(groups)
+            lib.crSetRenderMode(fused, 0)
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            rows = [er.renderPoseBatch(lib, p)[0].copy() for p in poses]
+            out[groups] = (np.concatenate(rows), er.getOmmatidialData(lib).copy(), states(S))
+        lib.setCurrentEyeSamplesPerOmmatidium(S)
+        loop = []
+        for p in np.concatenate(poses):
+            lib.setCameraPosition(*[float(v) for v in p[:3]])
+            lib.renderFrame()
+            loop.append(er.getFrame(lib, N, 1)[0].copy())
+        lib.setCameraPosition(*[float(v) for v in pose0[:3]])
+        assert np.array_equal(out[0][0], np.stack(loop)), (fused, "ungrouped batches vs the frame loop")
+        for k, name in enumerate(("rows", "float RGB", "stream states")):
+            assert np.array_equal(out[0][k].view(np.uint8), out[1][k].view(np.uint8)), (fused, name)
+        assert np.array_equal(out[1][2], states(S)), (fused, "states after the frame loop")
     lib.crSetRenderMode(0, 0)
 
 
