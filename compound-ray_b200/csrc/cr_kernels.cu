@@ -1296,9 +1296,19 @@ __global__ void __launch_bounds__(32 * kSumPartialWarps) k_sumPartials(const flo
         cy += __shfl_xor_sync(kFullMask, cy, d);
         cz += __shfl_xor_sync(kFullMask, cz, d);
     }
-    if (row < NF && l == 0) {
-        summed[row] = make_float4(cx, cy, cz, 0.0f);
-        if (fastRow != nullptr) sPx[rowInCta] = makeColor<FAST>(cx, cy, cz);
+    if (row < NF && l == 0) summed[row] = make_float4(cx, cy, cz, 0.0f);
+    if (fastRow != nullptr) {                                // (uniform)
+        if (lanesPerRow >= 4) {
+            // every lane of the row holds the three sums: lanes 0..2 gamma-encode one channel each (the pow is ~60 instructions)
+            constexpr float ex = static_cast<float>(1.0 / static_cast<double>(2.2f));
+            const float c = l == 0 ? cx : (l == 1 ? cy : cz);
+            const unsigned v = l < 3 ? (unsigned)static_cast<unsigned char>(Fn<FAST>::pow(fminf(fmaxf(c, 0.0f), 1.0f), ex) * 255.0f) : 0u;
+            const int base = lane - l;
+            const unsigned g = __shfl_sync(kFullMask, v, base + 1), b = __shfl_sync(kFullMask, v, base + 2);
+            if (row < NF && l == 0) sPx[rowInCta] = make_uchar4((unsigned char)v, (unsigned char)g, (unsigned char)b, 255u);
+        } else if (row < NF && l == 0) {
+            sPx[rowInCta] = makeColor<FAST>(cx, cy, cz);
+        }
     }
     if (fastRow == nullptr) return;                          // (uniform)
     __syncthreads();
