@@ -624,7 +624,8 @@ __device__ __forceinline__ Hit traceList(const float4* __restrict__ nodesAll, si
             }
         }
     }
-    if (COUNT) { *nodeCount = n; *triCount = tc; }
+    __syncwarp();                                                   // every lane is done with the refs: the next frame may be a per-lane
+    if (COUNT) { *nodeCount = n; *triCount = tc; }                  // walk, whose stack level 0 is this very row (racecheck, r03b)
     return best;
 }
 

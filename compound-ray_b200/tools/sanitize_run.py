@@ -27,6 +27,22 @@ for scene, cam in (("data/test-scene/test-scene.gltf", b"insect-cam-2"), ("data/
             lib.setCurrentEyeShaderName(b"single_dimension_fast"); er.setRenderSize(lib, N, 1)
             poses = er.make_poses(np.random.default_rng(S).uniform(-1, 1, (7, 3)))
             er.renderPoseBatch(lib, poses)
+    # round 2: fused / fast modes, candidate lists, wavefront queue, static split, frame groups, read-ahead, zero-copy rows
+    lib.setCurrentEyeShaderName(b"single_dimension_fast"); er.setRenderSize(lib, N, 1)
+    for fused, fast, lists, wavefront, dynamic in ((1, 0, 2, 0, 1), (1, 1, 2, 1, 1), (0, 0, 2, 1, 0), (1, 0, 0, 0, 0)):
+        lib.crSetRenderMode(fused, fast); lib.crDebugSetCandidateLists(lists)
+        lib.crDebugSetWavefront(wavefront, 7, 0.05); lib.crDebugSetDynamicChunks(dynamic)
+        for S in (32, 96, 40):
+            lib.setCurrentEyeSamplesPerOmmatidium(S)
+            for k in range(4):                                       # moving camera: zero-copy rows (fused), per-frame kernels
+                lib.setCameraPosition(0.1 * k, 0.2, 0.05 * k); lib.renderFrame(); lib.getFramePointer()
+            for k in range(9):                                       # standing camera: read-ahead launches, then a move drops the rest
+                lib.renderFrame(); lib.getFramePointer()
+            lib.setCameraPosition(0.3, 0.1, 0.0); lib.renderFrame(); lib.getFramePointer()
+            for n in (9, 5, 12):                                     # batches at even and odd starts: frame groups on and off
+                er.renderPoseBatch(lib, er.make_poses(np.random.default_rng(n).uniform(-1, 1, (n, 3))))
+            st = np.zeros((N * S, 8), np.uint32); lib.crDebugCopyRngStates(st.ctypes.data)
+    lib.crSetRenderMode(0, 0); lib.crDebugSetCandidateLists(0); lib.crDebugSetWavefront(0, 24, 0.35); lib.crDebugSetDynamicChunks(1)
     lib.crSetFirstFrame(3); lib.renderFrame(); lib.crSetFirstFrame(0)
     lib.crSetOmmatidialShard(5 * N, N); lib.renderFrame(); lib.crSetOmmatidialShard(0, 0)
     lib.crDebugSetRayDump(True); lib.renderFrame(); lib.crDebugSetRayDump(False)
