@@ -312,6 +312,27 @@ def test_product_reproduces_the_viewer_screenshot(lib, er, oracle, loader, ref_d
     # measured on a B200: 95.8 % exact (ground 91.9 %), 99.992 % within one step
     print(f"product vs reference screenshot: {(diff == 0).mean():.4f} exact, {(diff <= 1).mean():.5f} within one step; "
           f"ground {(diff[ground] == 0).mean():.4f} exact")
+    # ... and in the opt-in fast-math mode (hardware sin/cos/log/pow: what the reference's own --use_fast_math build runs,
+    # CMakeLists.txt:142): held to the same bound, and its share of byte-exact pixels is recorded next to the IEEE mode's
+    #  in gpurun_out/ when that directory exists.
+    lib.crSetRenderMode(0, 1)
+    try:
+        assert lib.renderFrame() > 0
+        lib.saveFrameAs(str(tmp_path / "panorama_fast.ppm").encode())
+    finally:
+        lib.crSetRenderMode(0, 0)
+    fast = read_ppm(str(tmp_path / "panorama_fast.ppm"))
+    d = np.abs(fast.astype(np.int32) - frame.astype(np.int32)).max(axis=2)      # a silhouette pixel may change sides: a fraction, not a max
+    assert (d <= 1).mean() >= 0.9995, (d <= 1).mean()
+    dfast = hold_to_screenshot(fast, ground, viewer_screenshot(lib, ref_outputs), 1)
+    line = (f"viewer screenshot, 160 000 pixels: IEEE mode {(diff == 0).mean():.4f} exact ({(diff[ground] == 0).mean():.4f} of the ground), "
+            f"fast-math mode {(dfast == 0).mean():.4f} exact ({(dfast[ground] == 0).mean():.4f} of the ground); "
+            f"within one step {(diff <= 1).mean():.5f} / {(dfast <= 1).mean():.5f}")
+    print(line)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "viewer_screenshot_ieee_vs_fast_math.txt"), "w") as f:
+            f.write(line + "\n")
 
 
 # ------------------------------------------------------------------------------------------ product (GPU)
