@@ -1,7 +1,7 @@
 #!/bin/bash
-# 8-GPU box: the driver's torchrun launch of bench.py at N = 8, 4, 2 (per-rank diagnostics), reference arm, cfg5 as one job.
+# 8-GPU box, final round-2 tree: the driver's torchrun launch of bench.py at N = 8, 4, 2, 1, reference arm, cfg5 as one job.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r02s}
+T=${TAG:-r03g}
 mkdir -p gpurun_out
 for N in 8 4 2; do
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N"
