@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r03f}
+T=${TAG:-r03l}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_reference_outputs.py -x -q -m gpu -s -k "fast_math_mode or viewer_screenshot" > gpurun_out/${T}_fast_tests_full.log 2>&1; echo "rc=$?"
-grep -v "^\[PyEye\]\|^WARNING\|^ERROR: Unable" gpurun_out/${T}_fast_tests_full.log | tail -12 | cut -c1-260
-cat gpurun_out/reference_frames_ieee_vs_fast_math.txt
+timeout 900 python benchmarks/pose_batch.py --poses 100000 --samples 64 --native --chunk 2048 --mode fused > gpurun_out/${T}_pose_batch_100k_native_1gpu.json 2> gpurun_out/${T}_pose_batch.log; cut -c1-600 gpurun_out/${T}_pose_batch_100k_native_1gpu.json
+timeout 600 python -m pytest tests/test_gpu_configs.py tests/test_sharding.py -x -q -m gpu 2>&1 | tail -3

@@ -33,6 +33,7 @@ def main():
                     "every rank passes all poses; the C++ host shards, positions the streams and gathers")
     ap.add_argument("--id-file", default=None, help="--native without torch.distributed: file that carries the NCCL unique id")
     ap.add_argument("--mode", default="ordered", choices=["ordered", "fused", "fused_fast"])
+    ap.add_argument("--reps", type=int, default=3, help="--native: repetitions of the whole job; `seconds` is their median")
     args = ap.parse_args()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -68,7 +69,12 @@ def main():
     all_poses = er.make_poses(pos, x=pose[3:6], y=pose[6:9], z=pose[9:12])
     poses = all_poses[lo:hi]
     lib.crSetFirstFrame(lo)
-    er.renderPoseBatch(lib, poses[:min(2048, len(poses))])                   # warm-up: allocations, module load, clocks (then rewind the streams)
+    # warm-up: allocations, module load and -- a fresh process on an idle GPU needs several hundred ms of load before a batch
+    # runs at its steady rate (the same 100 000 poses take 1.55 s in a process that has been rendering, 2.1-2.6 s right
+    # after start-up: profiles/r03h_small_batch_ab_100k.json) -- clocks; then rewind the streams
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 1.5:
+        er.renderPoseBatch(lib, poses[:min(4096, len(poses))])
     lib.crSetFirstFrame(lo)
     if args.native:
         sharding.init_library_comm(lib, rank, world, dist if use_torch else None, args.id_file)
@@ -81,18 +87,23 @@ def main():
             torch.cuda.synchronize()
         except Exception:
             pass
-        if use_torch:
-            dist.barrier()
-        t0 = time.perf_counter()
-        if dev_out is not None:
-            sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk, out_device_ptr=dev_out.data_ptr())
-        else:
-            rows, _ = sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk)   # all P rows on every rank, host side
-        dt = time.perf_counter() - t0
-        if use_torch:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        reps = []
+        for rep in range(args.reps):                 # the same logical job, repeated (streams repositioned at frame 0 by the call itself)
+            if use_torch:
+                dist.barrier()
+            t0 = time.perf_counter()
+            if dev_out is not None:
+                sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk, out_device_ptr=dev_out.data_ptr())
+            else:
+                rows, _ = sharding.render_pose_batch_sharded(lib, all_poses, chunk=args.chunk)   # all P rows on every rank, host side
+            dt = time.perf_counter() - t0
+            if use_torch:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            reps.append(dt)
+        dt = float(np.median(reps))
+        all_reps = reps
         checksum = int(dev_out.to(torch.int64).sum().item()) if dev_out is not None else int(rows.astype(np.int64).sum())
         lib.crCommDestroy()
     elif args.chunk > 0:
@@ -152,7 +163,7 @@ def main():
         out = {"benchmark": "pose batch (BASELINE config 5)", "n_gpus": world, "poses": P, "ommatidia": N, "samples": S,
                "chunk": args.chunk, "mode": args.mode,
                "data_plane": "library (crRenderPoseBatchSharded: ncclBroadcast groups per chunk, C++)" if args.native else "torch.distributed", "seconds": dt, "poses_per_sec": P / dt, "rays_per_sec": P * N * S / dt, "ommatidia_frames_per_sec": P * N / dt,
-               "checksum": checksum, "timing": "host wall clock incl. pose upload, render and gather; every rank ends with all rows in DEVICE memory; max over ranks"}
+               "seconds_all_repetitions": locals().get("all_reps"), "checksum": checksum, "timing": "host wall clock incl. pose upload, render and gather; every rank ends with all rows in DEVICE memory; max over ranks"}
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if use_torch:
         dist.destroy_process_group()

@@ -944,6 +944,11 @@ void Renderer::dropReadAhead(CompoundState& cs)
     if (cs.ahead.count > cs.ahead.next) {                // the streams ran ahead of the caller: rewind at the next prepareCompound
         cs.needRewind = true;
         cs.rewindTo = cs.frameIndex;
+        // Frames were rendered for nothing and a rewind is due: this caller does not stand still for long.  Ask for a
+        // longer standing streak before the next read-ahead (doubling, so a "k frames per pose" pattern stops paying after
+        // a few poses) and start again with a short batch.
+        cs.aheadStreakNeeded = std::min(4096, 2 * cs.aheadStreakNeeded + 2);
+        cs.aheadFrames = 4;
     }
     cs.ahead.count = cs.ahead.next = 0;
 }
@@ -959,6 +964,10 @@ bool Renderer::consumeReadAhead(CompoundState& cs, const HostCamera& cam, bool e
                       memcmp(&a.pose, &pose, sizeof(DevicePose)) == 0;
     if (!same) { dropReadAhead(cs); return false; }
     const size_t f = static_cast<size_t>(a.next++);
+    if (a.next == a.count) {                             // consumed to the end: the next batch may be twice as long, and the streak rule relaxes
+        cs.aheadFrames = std::min(64, 2 * cs.aheadFrames);
+        cs.aheadStreakNeeded = std::max(2, cs.aheadStreakNeeded / 2);
+    }
     memcpy(hFrame_, cs.hAheadRows + sizeof(uchar4) * f * static_cast<size_t>(cs.N), sizeof(uchar4) * static_cast<size_t>(a.rowPixels));
     hostFrameFresh_ = true;                              // the pinned host frame holds this frame; the device frame does not
     hostMirrorsDevice_ = false;
@@ -974,9 +983,11 @@ bool Renderer::consumeReadAhead(CompoundState& cs, const HostCamera& cam, bool e
 // possible now (the caller renders one frame the usual way).
 bool Renderer::launchReadAhead(CompoundState& cs, const HostCamera& cam)
 {
-    if (cs.standingFrames < 2 || cs.lastSingleFrameMs <= 0.0) return false;
+    if (cs.standingFrames < cs.aheadStreakNeeded || cs.lastSingleFrameMs <= 0.0) return false;
     const bool fused = fusedActive(cs, cam);
+    // batches start short and double while they are consumed to the end (cs.aheadFrames), up to the GPU-time budget
     size_t F = static_cast<size_t>(std::min(64.0, readAheadBudgetMs / std::max(cs.lastSingleFrameMs, 1e-3)));
+    F = std::min<size_t>(F, static_cast<size_t>(cs.aheadFrames));
     F = std::min(F, batchFramesPerLaunch(cs, F, fused));
     if (F < 2) return false;
     const size_t N = static_cast<size_t>(cs.N);

@@ -56,6 +56,8 @@ struct CompoundState {                 // device side of one CompoundEye camera
         double traceMsPerFrame = 0.0;
     } ahead;
     bool needRewind = false; uint64_t rewindTo = 0;
+    int aheadFrames = 4;               // frames of the next read-ahead launch: doubles while batches are consumed to the end, back to 4 after a drop
+    int aheadStreakNeeded = 2;         // standing frames required before a read-ahead: doubles whenever rendered frames had to be dropped
     uchar4* dAheadRows = nullptr; unsigned char* hAheadRows = nullptr; size_t aheadRowCap = 0;   // [frames][N] 8-bit rows, device + pinned host
     double lastSingleFrameMs = 0.0;                      // host time of the last frame rendered on its own
     // wavefront queue (k_traceCompound -> k_traceQueue -> k_shadeQueue): rays of the warp-frames without a candidate list

@@ -145,6 +145,10 @@ def init_library_comm(lib, rank: int, world: int, dist=None, id_path: str | None
     import ctypes as C
     import numpy as np
     buf = np.zeros(128, np.uint8)
+    if world == 1:                       # one rank gathers nothing: leave NCCL unloaded (crCommInit with one rank creates no communicator;
+        if lib.crCommInit(buf.ctypes.data_as(C.c_void_p), 1, 0) != 0:    # merely asking NCCL for a unique id -- its bootstrap thread -- made a
+            raise RuntimeError("crCommInit failed")                      # long single-GPU job 40 % slower: profiles/r03l vs r03k)
+        return
     if rank == 0:
         if lib.crCommGetUniqueId(buf.ctypes.data_as(C.c_void_p)) != 0:
             raise RuntimeError("crCommGetUniqueId failed (NCCL not loadable?)")
