@@ -123,7 +123,9 @@ void crSetOmmatidialShard(uint64_t globalCount, uint64_t firstIndex);
 /* Rank 0: fills the 128-byte NCCL unique id, which the launcher passes to every rank by its own means (MPI,
  * torch.distributed broadcast, a file). */
 int crCommGetUniqueId(void* out128);
-/* Every rank, collectively: joins the communicator on the library's device (crSetDevice first). */
+/* Every rank, collectively: joins the communicator on the library's device (crSetDevice first).  nRanks == 1 creates no
+ * communicator and does not touch NCCL (id128 is ignored; do not call crCommGetUniqueId for it either: a one-rank job then
+ * runs exactly as without the data plane). */
 int crCommInit(const void* id128, int nRanks, int rank);
 void crCommDestroy(void);
 int crCommRank(void);                 /* 0 without a communicator */
