@@ -117,7 +117,7 @@ public:
     bool frameGroups = true;           // batched launches of small frames: units of (32 rays, a group of frames) instead of (32 rays, all frames)
     bool readAhead = true;
     double readAheadBudgetMs = 1.5;
-    long long readAheadMaxRays = 2ll << 20;
+    long long readAheadMaxRays = 4ll << 20;   // (a rewind re-initialises every stream: 0.65 ms per million)
     bool standingFrontier = true;      // small frames: build the frontier once the camera has stood still for three frames, then reuse it
     bool spinSync = false;             // cudaDeviceScheduleSpin (CR_SPIN_SYNC=1, before the first GPU use)
     int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)

@@ -225,7 +225,7 @@ void crDebugSetNodeLanes(int lanes);
  * group step the launch's starting stream states over the draws of the frames before it.  Same frames bit for bit. */
 void crDebugSetFrameGroups(int on);
 /* Read-ahead for a standing camera (default on): once three consecutive renderFrame calls found the same pose, eye and
- * sample count, the following single_dimension_fast frames of up to 2M rays are rendered several at a time in one
+ * sample count, the following single_dimension_fast frames of up to 4M rays are rendered several at a time in one
  * batched launch of at most `budgetMs` (default 1.5; <= 0 keeps it) and handed out one per call; anything that changes
  * (pose, eye, samples, mode, size, a batch call, crSetFirstFrame ...) drops what is left and rewinds the sample streams to
  * the frame the caller has reached.  The frames are those of one-at-a-time rendering bit for bit; renderFrame's return
