@@ -1,6 +1,12 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r03l}
+T=${TAG:-r03o}
 mkdir -p gpurun_out
-timeout 900 python benchmarks/pose_batch.py --poses 100000 --samples 64 --native --chunk 2048 --mode fused > gpurun_out/${T}_pose_batch_100k_native_1gpu.json 2> gpurun_out/${T}_pose_batch.log; cut -c1-600 gpurun_out/${T}_pose_batch_100k_native_1gpu.json
-timeout 600 python -m pytest tests/test_gpu_configs.py tests/test_sharding.py -x -q -m gpu 2>&1 | tail -3
+V=$PWD/compound-ray_b200/lib/variants
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_modes.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -2
+run() { name=$1; shift
+  env "$@" timeout 600 python benchmarks/wavefront_sweep.py --modes 1:0 --refills 12 --node-lanes 8 --out gpurun_out/${T}_ab_${name}.json > gpurun_out/${T}_ab_${name}.log 2>&1; echo "$name rc=$?"; }
+run skysetup CR_X=1
+run base CR_LIB_PATH=$V/libEyeRenderer3_base.so
+run skysetup2 CR_X=1
+run base2 CR_LIB_PATH=$V/libEyeRenderer3_base.so

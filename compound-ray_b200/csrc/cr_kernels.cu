@@ -1084,8 +1084,12 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
                     h = traceClosestPhased<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
                                                  &nNode, &nTri, entry, ep.nodeLanes);
 #else
-                    h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
-                                           &nNode, &nTri, entry);
+                    if (entry.x == kSentinel) {             // empty frontier (the cone reaches nothing: sky): no box-test set-up either
+                        h.t = kTMax; h.prim = -1; h.u = 0.0f; h.v = 0.0f;
+                    } else {
+                        h = traceClosest<DUMP>(sc.nodes, sc.nodeVariantStride, sc.tris, ray, kTMax, &sStack[0][threadIdx.x], kTraceThreads,
+                                               &nNode, &nTri, entry);
+                    }
 #endif
                 }
             }
