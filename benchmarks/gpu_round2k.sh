@@ -1,12 +1,12 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r03o}
+T=${TAG:-r03p}
 mkdir -p gpurun_out
 V=$PWD/compound-ray_b200/lib/variants
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_modes.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -2
 run() { name=$1; shift
-  env "$@" timeout 600 python benchmarks/wavefront_sweep.py --modes 1:0 --refills 12 --node-lanes 8 --out gpurun_out/${T}_ab_${name}.json > gpurun_out/${T}_ab_${name}.log 2>&1; echo "$name rc=$?"; }
-run skysetup CR_X=1
-run base CR_LIB_PATH=$V/libEyeRenderer3_base.so
-run skysetup2 CR_X=1
-run base2 CR_LIB_PATH=$V/libEyeRenderer3_base.so
+  env "$@" timeout 600 python benchmarks/wavefront_sweep.py --modes 1:0,0:0 --refills 12 --node-lanes 8 --out gpurun_out/${T}_ab_${name}.json > gpurun_out/${T}_ab_${name}.log 2>&1; echo "$name rc=$?"; }
+run cpasync CR_X=1
+run base CR_LIB_PATH=$V/libEyeRenderer3_nocpasync.so
+run cpasync2 CR_X=1
+run base2 CR_LIB_PATH=$V/libEyeRenderer3_nocpasync.so
