@@ -344,6 +344,26 @@ T* dalloc(size_t n)
     CR_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
     return p;
 }
+// The build's temporaries come from the device's stream-ordered pool (kept between builds: release threshold = everything):
+// cudaMalloc / cudaFree cost milliseconds each and made the reported build time mostly allocator time.
+template <typename T>
+T* talloc(size_t n, cudaStream_t stream)
+{
+    static bool poolReady = false;
+    if (!poolReady) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        poolReady = true;
+    }
+    T* p = nullptr;
+    CR_CUDA(cudaMallocAsync(&p, sizeof(T) * (n ? n : 1), stream));
+    return p;
+}
 
 }  // namespace
 
@@ -406,18 +426,18 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
     if (!(perAxis && atoi(perAxis) != 0))
         for (int a = 0; a < 3; a++) bc.invExt[a] = extMax > 0.0f ? 1.0f / extMax : 0.0f;
 
-    float4* leafMin = dalloc<float4>(n);
-    float4* leafMax = dalloc<float4>(n);
-    unsigned long long* keysA = dalloc<unsigned long long>(n);
-    unsigned long long* keysB = dalloc<unsigned long long>(n);
-    uint32_t* valsA = dalloc<uint32_t>(n);
-    uint32_t* valsB = dalloc<uint32_t>(n);
+    float4* leafMin = talloc<float4>(n, stream);
+    float4* leafMax = talloc<float4>(n, stream);
+    unsigned long long* keysA = talloc<unsigned long long>(n, stream);
+    unsigned long long* keysB = talloc<unsigned long long>(n, stream);
+    uint32_t* valsA = talloc<uint32_t>(n, stream);
+    uint32_t* valsB = talloc<uint32_t>(n, stream);
     const int tpb = 256;
     const int gridN = (n + tpb - 1) / tpb;
     k_triBoundsMorton<<<gridN, tpb, 0, stream>>>(dPositions, dIndices, n, bc, leafMin, leafMax, keysA, valsA);
 
     const int numBlocks = (n + kSortTile - 1) / kSortTile;
-    uint32_t* blockHist = dalloc<uint32_t>((size_t)256 * numBlocks + 512);   // + 256 row totals + 256 digit bases
+    uint32_t* blockHist = talloc<uint32_t>((size_t)256 * numBlocks + 512, stream);   // + 256 row totals + 256 digit bases
     uint32_t* rowTotal = blockHist + (size_t)256 * numBlocks;
     uint32_t* digitBase = rowTotal + 256;
     for (int pass = 0; pass < 8; pass++) {
@@ -434,8 +454,8 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
     out.tris = dalloc<float4>((size_t)3 * n);
     k_emitTris<<<gridN, tpb, 0, stream>>>(dPositions, dIndices, n, valsA, out.tris);
 
-    float4* boxMin = dalloc<float4>((size_t)2 * n);
-    float4* boxMax = dalloc<float4>((size_t)2 * n);
+    float4* boxMin = talloc<float4>((size_t)2 * n, stream);
+    float4* boxMax = talloc<float4>((size_t)2 * n, stream);
     if (n == 1 || n <= leafSize) {
         // whole scene in one leaf: reduce the leaf boxes on the host (tiny)
         std::vector<float4> hMin(n), hMax(n);
@@ -453,10 +473,10 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
         out.nodes = dalloc<float4>(4 * 8);
         k_emitSingleRoot<<<1, 1, 0, stream>>>(n, boxMin, boxMax, out.nodes);
     } else {
-        int* parent = dalloc<int>((size_t)2 * n);
-        int2* children = dalloc<int2>(n);
-        int2* ranges = dalloc<int2>(n);
-        int* arrivals = dalloc<int>(n);
+        int* parent = talloc<int>((size_t)2 * n, stream);
+        int2* children = talloc<int2>(n, stream);
+        int2* ranges = talloc<int2>(n, stream);
+        int* arrivals = talloc<int>(n, stream);
         CR_CUDA(cudaMemsetAsync(arrivals, 0, sizeof(int) * n, stream));
         const int gridI = (n - 1 + tpb - 1) / tpb;
         k_buildHierarchy<<<gridI, tpb, 0, stream>>>(keysA, n, parent, children, ranges);
@@ -465,12 +485,14 @@ BvhBuildResult buildLbvh(const float* dPositions, const uint32_t* dIndices, int 
         out.nodes = dalloc<float4>((size_t)4 * (n - 1) * 8);
         k_emitNodes<<<gridI, tpb, 0, stream>>>(n, children, ranges, boxMin, boxMax, leafSize, out.nodes, (size_t)4 * (n - 1));
         CR_CUDA(cudaStreamSynchronize(stream));
-        cudaFree(parent); cudaFree(children); cudaFree(ranges); cudaFree(arrivals);
+        cudaFreeAsync(parent, stream); cudaFreeAsync(children, stream); cudaFreeAsync(ranges, stream); cudaFreeAsync(arrivals, stream);
     }
     CR_CUDA(cudaStreamSynchronize(stream));
     CR_CUDA(cudaGetLastError());
-    cudaFree(leafMin); cudaFree(leafMax); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
-    cudaFree(blockHist); cudaFree(boxMin); cudaFree(boxMax);
+    cudaFreeAsync(leafMin, stream); cudaFreeAsync(leafMax, stream); cudaFreeAsync(keysA, stream); cudaFreeAsync(keysB, stream);
+    cudaFreeAsync(valsA, stream); cudaFreeAsync(valsB, stream);
+    cudaFreeAsync(blockHist, stream); cudaFreeAsync(boxMin, stream); cudaFreeAsync(boxMax, stream);
+    CR_CUDA(cudaStreamSynchronize(stream));
     out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return out;
 }
