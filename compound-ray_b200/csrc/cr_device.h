@@ -97,6 +97,12 @@ struct EyeParams {
     int chunkUnits = 1;                  // units of 32 rays per work-counter fetch of the single-frame trace kernel
     unsigned* workCounter = nullptr;     // [0] chunks of ray units handed out beyond every warp's first, [1] warps that have left the
                                          // kernel (the last one zeroes both for the next launch); nullptr: static split
+    // SM-affine hand-out (round 2): blocks of 32 consecutive units go to ONE SM, whose warps share them through a per-SM ticket
+    // counter -- at S = 1024 the 32 resident warps of an SM then trace the 32 x 32 samples of one ommatidium together, so the nodes
+    // its cone reaches are fetched into that SM's L1 once instead of into 32 different ones.
+    unsigned* smSeq = nullptr;           // [smSlots] tickets handed out per slot (slot = SM); zeroed by the last warp to leave
+    unsigned long long* smTab = nullptr; // [smSlots][smCap]: (launch epoch << 32 | block of 32 units) of the slot's j-th block
+    unsigned smSlots = 0, smCap = 0, smEpoch = 0;
     int queueRefillBelow = 24;           // k_traceQueue fetches new rays when fewer lanes than this are still walking
     int nodeLanes = 16;                  // phase switch of the per-lane BVH walk: leave the node loop for the pending leaves when
                                          // fewer lanes than this still want a node (1 = classic while-while)
@@ -150,5 +156,6 @@ void launchTraceRays(const DeviceScene& sc, const float* origins, const float* d
 void launchSampleTexture(unsigned long long tex, const float* uv, int n, float4* out, cudaStream_t stream);
 void launchEvalMath(int fn, const float* a, const float* b, float* out, int n, cudaStream_t stream);
 int traceKernelOccupancy();   // resident CTAs per SM for the compound trace kernel
+unsigned deviceSmIdLimit(cudaStream_t stream);   // %nsmid: SM identifiers are below this (they need not be contiguous)
 
 }  // namespace cr

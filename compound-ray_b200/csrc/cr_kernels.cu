@@ -976,19 +976,72 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     const unsigned rayUnits = (total + 31u) >> 5;
     const unsigned groups = (MULTI && GROUPED) ? (unsigned)max(1, ep.frameGroups) : 1u;
     const unsigned nUnits = rayUnits * groups;
-    const unsigned chunkUnits = MULTI ? 1u : (unsigned)max(1, ep.chunkUnits);
+    const unsigned chunkUnits = (MULTI || ep.smSeq != nullptr) ? 1u : (unsigned)max(1, ep.chunkUnits);
     const unsigned nChunks = (nUnits + chunkUnits - 1u) / chunkUnits;
     // Two chunks are known ahead (the first two of every warp by its position in the grid): while chunk i is traced, the
     // RNG state of chunk i+1 is already on its way to L2 and the counter is asked for chunk i+2.
+    //
+    // SM-affine hand-out (ep.smSeq != nullptr; chunkUnits = 1): the global counter hands out BLOCKS of 32 consecutive units and
+    // a block belongs to one slot (an SM).  A warp draws a ticket k from its slot's counter: block
+    // j = k / 32 of the slot, unit k % 32 of that block.  Whoever draws the first ticket of a block fetches the block's number
+    // from the global counter and publishes it in smTab[slot][j] tagged with the launch's epoch (so the table is never cleared);
+    // the other 31 ticket holders read it there -- one or two units later, because tickets, like chunks, are drawn two ahead.
+    // Every unit is still traced exactly once and a ray's result does not depend on who traces it: no bit changes.
+    // Termination: block numbers need not grow with j (two warps may reach the global counter out of order), so a warp leaves
+    // only when BOTH units it holds are beyond the end, and draws a new ticket only while its current unit is real -- the warp
+    // that holds the last real ticket of a slot keeps drawing until the slot's sequence runs into a block beyond the end.
+    // Tickets per slot <= units + 2 per warp, hence j < units/32 + gridWarps/16 + 2 <= smCap (sized by the host).
+    const bool smMode = ep.smSeq != nullptr;                               // (uniform)
+    // (the slot is read once: re-reading %smid per ticket measured slower -- 23.4 vs 24.3 Grays/s batched -- and a first version
+    //  that derived it with two integer modulos per unit spent 5 % of the per-frame kernel's instructions on them)
+    unsigned mySlot = 0u;
+    if (smMode) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        mySlot = min(smid, ep.smSlots - 1u);                               // (smSlots = %nsmid: the clamp never acts)
+    }
+    auto takeTicket = [&]() -> unsigned {                                  // (lane 0)
+        const unsigned slot = mySlot;
+        const unsigned k = atomicAdd(ep.smSeq + slot, 1u);
+        if ((k & 31u) == 0u) {
+            const unsigned nb = atomicAdd(ep.workCounter, 1u);
+            if ((k >> 5) >= ep.smCap) __trap();                            // (cannot happen: see the bound above)
+            __stcg(ep.smTab + (size_t)slot * ep.smCap + (k >> 5), ((unsigned long long)ep.smEpoch << 32) | nb);
+        }
+        return k;
+    };
+    auto unitOfTicket = [&](unsigned k) -> unsigned {                      // (lane 0)
+        if (k == 0xffffffffu) return 0xffffffffu;
+        const unsigned nBlocks32 = (nUnits + 31u) >> 5;
+        const volatile unsigned long long* p = ep.smTab + (size_t)mySlot * ep.smCap + (k >> 5);
+        unsigned long long v;
+        do { v = *p; } while ((unsigned)(v >> 32) != ep.smEpoch);
+        const unsigned nb = (unsigned)v;
+        return nb < nBlocks32 ? (nb << 5) + (k & 31u) : 0xffffffffu;
+    };
     unsigned chunk = blockIdx.x * (kTraceThreads / 32u) + (threadIdx.x >> 5);
     unsigned nextChunk = chunk + gridWarps;
-    while (chunk < nChunks) {                                              // (warp-uniform)
+    if (smMode) {                                                          // nextChunk holds a TICKET until the top of the loop
+        unsigned t0 = 0u, t1 = 0u;
+        if (lane == 0) { t0 = takeTicket(); t1 = takeTicket(); t0 = unitOfTicket(t0); }
+        chunk = __shfl_sync(kFullMask, t0, 0);
+        nextChunk = t1;
+    }
+    for (;;) {                                                             // (every branch on chunk / nextChunk is warp-uniform)
+      if (smMode) {
+          unsigned u = 0u;
+          if (lane == 0) u = unitOfTicket(nextChunk);
+          nextChunk = __shfl_sync(kFullMask, u, 0);
+          if (chunk >= nChunks && nextChunk >= nChunks) break;
+      } else if (chunk >= nChunks) break;
       unsigned afterNext = nextChunk + gridWarps;                           // static split when there is no counter
-      if (ep.workCounter != nullptr && lane == 0) afterNext = atomicAdd(ep.workCounter, 1u) + 2u * gridWarps;
+      if (smMode) { afterNext = 0xffffffffu; if (lane == 0 && chunk < nChunks) afterNext = takeTicket(); }
+      else if (ep.workCounter != nullptr && lane == 0) afterNext = atomicAdd(ep.workCounter, 1u) + 2u * gridWarps;
       if (groups == 1u) {
           const size_t rn = ((size_t)nextChunk * chunkUnits << 5) + (unsigned)lane;
           if (rn < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.rng + 2 * rn));
       }
+      if (chunk < nChunks)
       for (unsigned k = 0; k < chunkUnits; k++) {
         const unsigned unit = chunk * chunkUnits + k;
         if (unit >= nUnits) break;                                          // (warp-uniform)
@@ -1143,7 +1196,10 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     }
     // The last warp of the grid to leave rearms the counters for the next launch (no memset between frames).
     if (ep.workCounter != nullptr && lane == 0) {
-        if (atomicAdd(ep.workCounter + 1, 1u) == gridWarps - 1u) { atomicExch(ep.workCounter, 0u); atomicExch(ep.workCounter + 1, 0u); }
+        if (atomicAdd(ep.workCounter + 1, 1u) == gridWarps - 1u) {
+            atomicExch(ep.workCounter, 0u); atomicExch(ep.workCounter + 1, 0u);
+            if (smMode) for (unsigned i = 0; i < ep.smSlots; i++) atomicExch(ep.smSeq + i, 0u);
+        }
     }
 }
 
@@ -1769,6 +1825,25 @@ int traceKernelOccupancy()
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traceCompound<false, true, false, false>, kTraceThreads, 0);
     return n > 0 ? n : 1;
+}
+
+// Upper bound of %smid on this device (%nsmid).  SM identifiers need not be contiguous -- a B200 has 148 SMs but may number
+// them beyond 148 -- so the per-SM ticket slots of the trace kernel are sized by this, not by the SM count.
+__global__ void k_smIdLimit(unsigned* out)
+{
+    unsigned n;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = n;
+}
+unsigned deviceSmIdLimit(cudaStream_t stream)
+{
+    unsigned* d = nullptr;
+    unsigned h = 0;
+    if (cudaMalloc(&d, sizeof(unsigned)) != cudaSuccess) return 0;
+    k_smIdLimit<<<1, 1, 0, stream>>>(d);
+    if (cudaMemcpyAsync(&h, d, sizeof(unsigned), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) h = 0;
+    cudaFree(d);
+    return h;
 }
 
 void launchProjectVector(int mode, bool fast, const float4* summed, int N, uchar4* frame, int W, int H, cudaStream_t stream)

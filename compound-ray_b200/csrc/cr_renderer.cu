@@ -66,6 +66,7 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_ZERO_COPY")) zeroCopyFrames = atoi(e) != 0;
     if (const char* e = getenv("CR_DYNAMIC_CHUNKS")) dynamicChunks = atoi(e) != 0;
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
+    if (const char* e = getenv("CR_SM_AFFINE")) smAffine = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
     if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
     if (const char* e = getenv("CR_FRAME_GROUPS")) frameGroups = atoi(e) != 0;
@@ -139,6 +140,8 @@ void Renderer::freeCompound(CompoundState& cs)
     dfree(cs.dDumpO); dfree(cs.dDumpD); dfree(cs.dDumpH); dfree(cs.dDumpC);
     dfree(cs.dBatchSamples); dfree(cs.dBatchSummed); dfree(cs.dBatchPoses); dfree(cs.dEntries); dfree(cs.dPartials); dfree(cs.dLists);
     dfree(cs.dQueueRays); dfree(cs.dQueueHits); dfree(cs.dQueueWarps); dfree(cs.dQueueCounters);
+    dfree(cs.dSmSeq); dfree(cs.dSmTab);
+    cs.smSlots = cs.smCap = 0;
     dfree(cs.dAheadRows);
     if (cs.hAheadRows) cudaFreeHost(cs.hAheadRows);
     cs.hAheadRows = nullptr;
@@ -539,16 +542,51 @@ void Renderer::ensureQueue(CompoundState& cs, size_t frames)
     cs.queueCap = need;
 }
 
-// The queue takes the warp-frames that have no candidate list, so it exists only in launches that build the lists.
-void Renderer::attachQueue(CompoundState& cs, EyeParams& ep)
+// Work hand-out of the trace kernel.  counters: [0] rays pushed to the queue, [1] rays handed out by k_traceQueue (zeroed per
+// launch that has a queue); [2] work chunks handed out, [3] warps that left the trace kernel (zeroed once: the kernel rearms
+// them itself).  SM-affine hand-out on top of the counter when the launch has enough blocks of 32 units to keep every SM
+// busy: a ticket counter per slot (rearmed by the kernel) and the slot's block table, whose entries carry the launch's epoch.
+void Renderer::attachWorkCounter(CompoundState& cs, EyeParams& ep)
 {
-    // counters: [0] rays pushed to the queue, [1] rays handed out by k_traceQueue (zeroed per launch that has a queue);
-    // [2] work chunks handed out, [3] warps that left the trace kernel (zeroed once: the kernel rearms them itself)
     if (!cs.dQueueCounters) {
         cs.dQueueCounters = dallocT<unsigned>(4);
         CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 4, stream_));
     }
-    if (dynamicChunks) ep.workCounter = cs.dQueueCounters + 2;
+    if (!dynamicChunks) return;
+    ep.workCounter = cs.dQueueCounters + 2;
+    if (smAffine <= 0 || dumpRays) return;
+    const unsigned long long rayUnits = (static_cast<unsigned long long>(cs.N) * static_cast<unsigned long long>(cs.S) + 31ull) / 32ull;
+    const unsigned long long units = rayUnits * static_cast<unsigned long long>(std::max(1, ep.poses ? ep.frameGroups : 1));
+    const unsigned long long blocks = (units + 31ull) / 32ull;
+    if (smIdLimit_ == 0u) {
+        smIdLimit_ = std::max(static_cast<unsigned>(numSMs_), deviceSmIdLimit(stream_));
+        if (getenv("CR_SM_AFFINE_VERBOSE")) std::cerr << "[cr] SM ids below " << smIdLimit_ << " on " << numSMs_ << " SMs" << std::endl;
+    }
+    const unsigned slots = smIdLimit_;
+    const unsigned long long gridWarps = static_cast<unsigned long long>(numSMs_) * traceOcc_ * (kTraceThreads / 32);
+    const unsigned long long cap = blocks + gridWarps / 16ull + 2ull;
+    // enough blocks for the counter to balance the SMs (a block is what a unit is to a warp), and a table of sane size
+    if (blocks < static_cast<unsigned long long>(smAffine > 1 ? smAffine : 16) * static_cast<unsigned>(numSMs_) || cap * slots * 8ull > (128ull << 20)) return;
+    if (cs.smSlots != slots || cs.smCap < cap) {
+        dfree(cs.dSmSeq); dfree(cs.dSmTab);
+        cs.dSmSeq = dallocT<unsigned>(slots);
+        cs.dSmTab = dallocT<unsigned long long>(static_cast<size_t>(cap) * slots);
+        CR_CUDA(cudaMemsetAsync(cs.dSmSeq, 0, sizeof(unsigned) * slots, stream_));
+        CR_CUDA(cudaMemsetAsync(cs.dSmTab, 0, sizeof(unsigned long long) * static_cast<size_t>(cap) * slots, stream_));
+        cs.smSlots = slots; cs.smCap = static_cast<unsigned>(cap); cs.smEpoch = 0;
+    }
+    if (++cs.smEpoch == 0u) {              // epoch wrapped: entries of 2^32 launches ago could look current
+        CR_CUDA(cudaMemsetAsync(cs.dSmTab, 0, sizeof(unsigned long long) * static_cast<size_t>(cs.smCap) * cs.smSlots, stream_));
+        cs.smEpoch = 1u;
+    }
+    ep.smSeq = cs.dSmSeq; ep.smTab = cs.dSmTab;
+    ep.smSlots = cs.smSlots; ep.smCap = cs.smCap; ep.smEpoch = cs.smEpoch;
+}
+
+// The queue takes the warp-frames that have no candidate list, so it exists only in launches that build the lists.
+void Renderer::attachQueue(CompoundState& cs, EyeParams& ep)
+{
+    attachWorkCounter(cs, ep);
     ep.chunkUnits = std::max(1, chunkUnits);
     if (!wavefront || ep.lists == nullptr || dumpRays) return;
     if (static_cast<double>(ep.poses ? ep.nFrames : 1) * cs.N >= 2147483648.0) return;   // frame*N + ommatidium would not fit 31 bits
@@ -687,11 +725,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
         ep.nFrames = nFrames;
         ep.entryFrameStride = 0;
         ep.poses = dPoses;
-        if (!cs.dQueueCounters) {
-            cs.dQueueCounters = dallocT<unsigned>(4);
-            CR_CUDA(cudaMemsetAsync(cs.dQueueCounters, 0, sizeof(unsigned) * 4, stream_));
-        }
-        if (dynamicChunks) ep.workCounter = cs.dQueueCounters + 2;
+        attachWorkCounter(cs, ep);
         ep.chunkUnits = 1;
     } else {
         ep.poses = dPoses;

@@ -62,6 +62,8 @@ struct CompoundState {                 // device side of one CompoundEye camera
     double lastSingleFrameMs = 0.0;                      // host time of the last frame rendered on its own
     // wavefront queue (k_traceCompound -> k_traceQueue -> k_shadeQueue): rays of the warp-frames without a candidate list
     float4* dQueueRays = nullptr; int4* dQueueHits = nullptr; int* dQueueWarps = nullptr; unsigned* dQueueCounters = nullptr; size_t queueCap = 0;
+    // SM-affine hand-out of the trace kernel's work units (EyeParams::smSeq / smTab)
+    unsigned* dSmSeq = nullptr; unsigned long long* dSmTab = nullptr; unsigned smSlots = 0, smCap = 0, smEpoch = 0;
     // debug dump buffers
     float* dDumpO = nullptr; float* dDumpD = nullptr; int4* dDumpH = nullptr; int2* dDumpC = nullptr; size_t dumpCap = 0;
 };
@@ -123,6 +125,7 @@ public:
     int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)
     int chunkUnits = 1;                // single-frame trace kernel: units of 32 rays per counter fetch (larger chunks of one ommatidium's
                                        // units measured slower: 2 -> 623, 4 -> 723, 8 -> 993 us per headline frame)
+    int smAffine = 1;                  // trace kernel: blocks of 32 units stay on one SM (per-SM tickets, EyeParams::smSeq); needs dynamicChunks
     bool dynamicChunks = true;         // trace kernel: ray units handed out through a global counter instead of a static grid-stride split
     int wavefront = 0;
     int nodeLanes = 16;                // phase switch of the per-lane BVH walk (EyeParams::nodeLanes); 1 = classic while-while
@@ -189,6 +192,7 @@ private:
     void ensureQueue(CompoundState& cs, size_t frames);
     size_t queueRaysFor(const CompoundState& cs, size_t frames) const;
     void attachQueue(CompoundState& cs, EyeParams& ep);
+    void attachWorkCounter(CompoundState& cs, EyeParams& ep);
     bool entryFrontierActive(const CompoundState& cs, int frames) const;   // frames = poses covered by the launch
     void buildEntries(CompoundState& cs, EyeParams& ep);
     void project(CompoundState& cs, const HostCamera& cam);
@@ -206,6 +210,7 @@ private:
     cudaEvent_t evA_ = nullptr, evB_ = nullptr;
     cudaEvent_t evMark_[4] = {nullptr, nullptr, nullptr, nullptr};
     int numSMs_ = 148;
+    unsigned smIdLimit_ = 0;            // %nsmid of the device (deviceSmIdLimit), queried at the first SM-affine launch
     int traceOcc_ = 8;
 
     // device scene
