@@ -2,7 +2,7 @@
 # Evidence refresh for the final round-2 tree: all GPU tests, ncu captures for profiles/k1_traffic.json, full ncu of the batched and
 # per-frame trace kernels, bench lines, launch list, configs, speed-test protocol.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r03q}
+T=${TAG:-r04e}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu --durations=8 > gpurun_out/${T}_gpu_tests.log 2>&1; echo "all gpu tests rc=$?"
 tail -14 gpurun_out/${T}_gpu_tests.log | cut -c1-160
@@ -20,6 +20,8 @@ python profiles/make_k1_traffic.py $ARGS > gpurun_out/${T}_k1_traffic.txt 2>&1; 
 cp profiles/k1_traffic.json gpurun_out/${T}_k1_traffic.json
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_traceCompound -s 1 -c 1 -f -o gpurun_out/${T}_k1_batched_full \
    python bench.py --mode fused --steps 20 --repeats 1 --no-cpu-baseline --no-modes > gpurun_out/${T}_ncu_full_batched.log 2>&1; echo "ncu full batched rc=$?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_traceCompound -s 8 -c 1 -f -o gpurun_out/${T}_k1_perframe_full \
+   python bench.py --mode fused --steps 20 --repeats 1 --no-cpu-baseline --no-modes > gpurun_out/${T}_ncu_full_perframe.log 2>&1; echo "ncu full per-frame rc=$?"
 timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.log; echo "bench rc=$?"
 cut -c1-200 gpurun_out/${T}_bench.json
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench_steps20.json 2>> gpurun_out/${T}_bench.log; echo "bench20 rc=$?"

@@ -392,6 +392,7 @@ void crDebugFrameBreakdown(float* out3)
     CR_GUARD_END()
 }
 void crDebugSetDynamicChunks(int on) { renderer().dynamicChunks = on != 0; }
+void crDebugSetSmAffine(int on, int minBlocksPerSm) { renderer().smAffine = on != 0; renderer().smAffineMinBlocks = minBlocksPerSm; }
 void crDebugSetZeroCopy(int on) { renderer().zeroCopyFrames = on != 0; }
 unsigned long long crDebugLastQueuedRays()
 {

@@ -67,6 +67,7 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_DYNAMIC_CHUNKS")) dynamicChunks = atoi(e) != 0;
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
     if (const char* e = getenv("CR_SM_AFFINE")) smAffine = atoi(e);
+    if (const char* e = getenv("CR_SM_AFFINE_MIN_BLOCKS")) smAffineMinBlocks = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
     if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
     if (const char* e = getenv("CR_FRAME_GROUPS")) frameGroups = atoi(e) != 0;
@@ -566,7 +567,7 @@ void Renderer::attachWorkCounter(CompoundState& cs, EyeParams& ep)
     const unsigned long long gridWarps = static_cast<unsigned long long>(numSMs_) * traceOcc_ * (kTraceThreads / 32);
     const unsigned long long cap = blocks + gridWarps / 16ull + 2ull;
     // enough blocks for the counter to balance the SMs (a block is what a unit is to a warp), and a table of sane size
-    if (blocks < static_cast<unsigned long long>(smAffine > 1 ? smAffine : 16) * static_cast<unsigned>(numSMs_) || cap * slots * 8ull > (128ull << 20)) return;
+    if (blocks < static_cast<unsigned long long>(std::max(0, smAffineMinBlocks)) * static_cast<unsigned>(numSMs_) || cap * slots * 8ull > (128ull << 20)) return;
     if (cs.smSlots != slots || cs.smCap < cap) {
         dfree(cs.dSmSeq); dfree(cs.dSmTab);
         cs.dSmSeq = dallocT<unsigned>(slots);

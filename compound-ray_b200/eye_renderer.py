@@ -122,6 +122,7 @@ def configureFunctions(eyeRenderer):
     r.crDebugSetFrameProfile.argtypes = [C.c_int]
     r.crDebugFrameBreakdown.argtypes = [vp]
     r.crDebugSetDynamicChunks.argtypes = [C.c_int]
+    r.crDebugSetSmAffine.argtypes = [C.c_int, C.c_int]
     r.crDebugSetZeroCopy.argtypes = [C.c_int]
     r.crDebugLastQueuedRays.restype = C.c_ulonglong
     r.crDebugCopyCandidateLists.argtypes = [vp, C.c_size_t]

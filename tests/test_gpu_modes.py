@@ -37,6 +37,7 @@ def _default_modes(lib):
     lib.crDebugSetWavefront(0, 24, 0.35)
     lib.crDebugSetNodeLanes(16)
     lib.crDebugSetDynamicChunks(1)
+    lib.crDebugSetSmAffine(1, 16)
     lib.crDebugSetReadAhead(1, 1.5)
     lib.crDebugSetFrameGroups(1)
     lib.crDebugSetRayDump(False)
@@ -223,6 +224,57 @@ def test_wavefront_queue_changes_no_bit(lib, er, loader, oracle, terrain):
             for a, b in zip(out[(fused, "off")], out[(fused, key)]):
                 assert np.array_equal(a, b), (fused, key)
         assert np.array_equal(out[(fused, "off")][1][0], out[(fused, "off")][2][0])
+    lib.crSetRenderMode(0, 0)
+
+
+def test_sm_affine_hand_out_changes_no_bit(lib, er, loader, oracle, terrain):
+    """SM-affine hand-out of the trace kernel's units (blocks of 32 units stay on one SM through per-SM ticket counters, the
+    block numbers published in an epoch-tagged table): float RGB, 8-bit rows, pose-batch rows and the XORWOW states afterwards
+    are bit-identical with the hand-out off, on at its default threshold and forced on for launches of any size -- frames of
+    fewer blocks than SMs, a ragged last block, S not a multiple of 32, grouped and ungrouped batches, both reductions, many
+    launches in a row (the counters are rearmed by the kernel itself) -- and equal the oracle."""
+    lib.loadGlTFscene(terrain.encode())
+    assert lib.gotoCameraByName(b"compound-cam")
+    lib.setCurrentEyeShaderName(b"single_dimension_fast")
+    sc, sh, ocam = load_oracle_scene(loader, oracle, terrain, "compound-cam")
+    lib.crDebugSetReadAhead(0, 0.0)
+    pose0 = np.zeros(12, np.float32); lib.crDebugCopyCameraPose(pose0.ctypes.data)
+    poses = np.tile(pose0, (7, 1)); poses[:, 1] += np.float32([0.0, 0.25, 0.5, 1.0, 3.0, 9.0, 20.0])
+    # (N, S): 79 units = 3 blocks, the last one ragged; S = 40: rows straddle warps; 9 280 units = 290 blocks on 148 SMs;
+    # 2 500 x 128 = 10 000 units (313 blocks, > 2 per SM)
+    for N, S in ((63, 40), (1450, 200), (2320, 128), (2500, 128)):
+        omm = ocam.ommatidia[:: len(ocam.ommatidia) // N][:N]
+        er.setOmmatidiaFromArray(lib, omm)
+        er.setRenderSize(lib, N, 1)
+        eye = oracle.CompoundEyeOracle(sh, omm, oracle.pose_from_camera(ocam), "single_dimension_fast", samples=S)
+        eye.set_render_size(N, 1)
+        eye.render_frame(method="bvh")
+        want_seq = eye.last["summed"].copy()
+        want_fused = oracle.fused_sum(eye.last["compound"], N, S) if S % 32 == 0 else None
+        out = {}
+        for fused in (0, 1):
+            for key, (on, minb) in {"off": (0, 16), "default": (1, 16), "forced": (1, 0), "two": (1, 2)}.items():
+                lib.crSetRenderMode(fused, 0)
+                lib.crDebugSetSmAffine(on, minb)
+                lib.setCurrentEyeSamplesPerOmmatidium(S)               # restarts the streams at frame 0
+                frames = []
+                for _ in range(3):                                      # consecutive launches: counters rearmed, epochs advance
+                    lib.renderFrame()
+                    frames.append((er.getOmmatidialData(lib).copy(), er.getFrame(lib, N, 1).copy()))
+                rows, _ = er.renderPoseBatch(lib, poses)                # starts at frame 3 (odd): ungrouped
+                rows2, _ = er.renderPoseBatch(lib, poses[:6])           # starts at frame 10 (even): grouped when the frame is small
+                st = np.zeros((N * S, 8), np.uint32)
+                lib.crDebugCopyRngStates(st.ctypes.data)
+                out[(fused, key)] = (frames, rows.copy(), rows2.copy(), st)
+                want = want_fused if (fused and want_fused is not None) else want_seq
+                assert np.array_equal(frames[0][0].view(np.uint32), want.view(np.uint32)), (N, S, fused, key)
+            ref = out[(fused, "off")]
+            for key in ("default", "forced", "two"):
+                got = out[(fused, key)]
+                for (a0, a1), (b0, b1) in zip(ref[0], got[0]):
+                    assert np.array_equal(a0.view(np.uint32), b0.view(np.uint32)) and np.array_equal(a1, b1), (N, S, fused, key)
+                assert np.array_equal(ref[1], got[1]) and np.array_equal(ref[2], got[2]), (N, S, fused, key, "batch rows")
+                assert np.array_equal(ref[3], got[3]), (N, S, fused, key, "stream states")
     lib.crSetRenderMode(0, 0)
 
 
