@@ -38,6 +38,7 @@ def _default_modes(lib):
     lib.crDebugSetNodeLanes(16)
     lib.crDebugSetDynamicChunks(1)
     lib.crDebugSetSmAffine(1, 16)
+    lib.crDebugSetZeroCopy(1)
     lib.crDebugSetReadAhead(1, 1.5)
     lib.crDebugSetFrameGroups(1)
     lib.crDebugSetRayDump(False)
@@ -232,7 +233,8 @@ def test_sm_affine_hand_out_changes_no_bit(lib, er, loader, oracle, terrain):
     block numbers published in an epoch-tagged table): float RGB, 8-bit rows, pose-batch rows and the XORWOW states afterwards
     are bit-identical with the hand-out off, on at its default threshold and forced on for launches of any size -- frames of
     fewer blocks than SMs, a ragged last block, S not a multiple of 32, grouped and ungrouped batches, both reductions, many
-    launches in a row (the counters are rearmed by the kernel itself) -- and equal the oracle."""
+    launches in a row (the counters are rearmed by the kernel itself), with the 8-bit row written straight into the mapped host
+    frame or copied -- and equal the oracle."""
     lib.loadGlTFscene(terrain.encode())
     assert lib.gotoCameraByName(b"compound-cam")
     lib.setCurrentEyeShaderName(b"single_dimension_fast")
@@ -253,8 +255,10 @@ def test_sm_affine_hand_out_changes_no_bit(lib, er, loader, oracle, terrain):
         want_fused = oracle.fused_sum(eye.last["compound"], N, S) if S % 32 == 0 else None
         out = {}
         for fused in (0, 1):
-            for key, (on, minb) in {"off": (0, 16), "default": (1, 16), "forced": (1, 0), "two": (1, 2)}.items():
+            for key, (on, minb, zc) in {"off": (0, 16, 1), "default": (1, 16, 1), "forced": (1, 0, 1), "two": (1, 2, 1),
+                                        "copy": (1, 16, 0)}.items():
                 lib.crSetRenderMode(fused, 0)
+                lib.crDebugSetZeroCopy(zc)            # 8-bit row straight into the mapped host frame / device-to-host copy
                 lib.crDebugSetSmAffine(on, minb)
                 lib.setCurrentEyeSamplesPerOmmatidium(S)               # restarts the streams at frame 0
                 frames = []
@@ -269,7 +273,7 @@ def test_sm_affine_hand_out_changes_no_bit(lib, er, loader, oracle, terrain):
                 want = want_fused if (fused and want_fused is not None) else want_seq
                 assert np.array_equal(frames[0][0].view(np.uint32), want.view(np.uint32)), (N, S, fused, key)
             ref = out[(fused, "off")]
-            for key in ("default", "forced", "two"):
+            for key in ("default", "forced", "two", "copy"):
                 got = out[(fused, key)]
                 for (a0, a1), (b0, b1) in zip(ref[0], got[0]):
                     assert np.array_equal(a0.view(np.uint32), b0.view(np.uint32)) and np.array_equal(a1, b1), (N, S, fused, key)
