@@ -1,15 +1,13 @@
 #!/bin/bash
+# programmatic dependent launch (frontier pass -> trace -> reduction) + frontier pass v2 without the near/far swap: parity, A/B
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r04h}
+T=${TAG:-r04j}
 mkdir -p gpurun_out
-V=$PWD/compound-ray_b200/lib/variants
-run() { name=$1; shift
-  env "$@" timeout 600 python benchmarks/wavefront_sweep.py --modes 1:0 --refills 12 --node-lanes 8 --out gpurun_out/${T}_ab_${name}.json > gpurun_out/${T}_ab_${name}.log 2>&1; echo "$name rc=$?"
-  grep -E '"what": "(per frame, no lists)"' gpurun_out/${T}_ab_${name}.log | python -c "
-import sys, json
-for l in sys.stdin:
-    d = json.loads(l)
-    print('   ', d['what'], {k: round(v, 4) for k, v in d.items() if k in ('grays_device', 'ms_per_frame', 'per_frame_wall_ms', 'trace_ms', 'frontier_ms', 'reduce_ms', 'grays_per_frame_abi')}, d.get('rows_equal_first_variant'))"; }
-run nofinish CR_FUSED_FINISH=0
-run nofence CR_LIB_PATH=$V/libEyeRenderer3_nofence.so
-run nohostcopy CR_LIB_PATH=$V/libEyeRenderer3_nohostcopy.so
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_modes.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python compound-ray_b200/tools/frontier_fuzz.py --configs 200 --seed 12 2>&1 | tail -1
+for i in 1 2; do for pdl in 1 0; do
+env CR_PDL=$pdl timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-modes 2>/dev/null > gpurun_out/${T}_bench_pdl${pdl}_$i.json
+python -c "
+import json
+d=json.load(open('gpurun_out/${T}_bench_pdl${pdl}_$i.json')); print('bench pdl=$pdl: value %.2f e2e %.2f (%.4f ms) launches %s' % (d['value']/1e9, d['e2e']['value']/1e9, d['e2e']['ms_per_step'], d['gpu_launches']))"
+done; done

@@ -56,6 +56,7 @@ struct DeviceScene {
     int nNodes = 0;
     int nTris = 0;
     int missShader = 0;
+    float boundsAbsMax = 0.0f;      // largest |coordinate| of any node box (vertex bounds + the leaf padding): scale of the frontier pass's tolerance
 };
 
 struct alignas(16) DevicePose {
@@ -108,6 +109,7 @@ struct EyeParams {
                                          // fewer lanes than this still want a node (1 = classic while-while)
     float4* partials = nullptr;          // fused reduction: [nFrames][N][S/32] per-warp sums of 32 samples (K1 -> k_sumPartials)
     const int* lists = nullptr;          // [nFrames][N][16] candidate lists (k_buildEntries stage 2): header = element count, -1 = none
+    bool pdl = false;                    // launch the trace and reduction kernels as programmatic dependents of the kernel before them
     bool fused = false;                  // in-kernel reduction (needs S % 32 == 0) instead of the ordered per-sample buffer
     bool fast = false;                   // hardware elementary functions instead of cr_math.h
     DevicePose pose;

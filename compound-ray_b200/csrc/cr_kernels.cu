@@ -708,6 +708,9 @@ __device__ __forceinline__ uchar4 makeColorMode(bool fast, float r, float g, flo
 #ifndef CR_ENTRY_PREFETCH
 #define CR_ENTRY_PREFETCH 0   // measured: 46 us instead of 36 us per headline frame with the prefetch (the extra L1 fills cost more than they hide)
 #endif
+#ifndef CR_ENTRY_V2
+#define CR_ENTRY_V2 1         // descent with per-lane slots, ballots and the centre / half-extent cone test (0: the first form)
+#endif
 constexpr int kEntryK = 4;                      // slots of the int4 record
 constexpr int kEntryBudget = CR_ENTRY_BUDGET;   // entries actually handed out (<= kEntryK)
 
@@ -729,6 +732,31 @@ __device__ __forceinline__ bool coneMayTouchBox(const ConePyramid& P, const V3 b
     const float M = fmaxf(P.axis.x * lo.x, P.axis.x * hi.x) + fmaxf(P.axis.y * lo.y, P.axis.y * hi.y) + fmaxf(P.axis.z * lo.z, P.axis.z * hi.z);
     if (M < -tol) return false;                         // wholly behind the apex
     return true;
+}
+
+// The same test in centre / half-extent form (round 2, last session): least signed distance of the box to face i =
+// n_i.c - |n_i|.h, greatest extent along the axis = axis.c + |axis|.h, with c = box centre - apex, h = half extents.  52
+// instead of 91 instructions per child box, and axis.c is the sort key the pass needs anyway.  The tolerance is one constant
+// per ommatidium -- 2^-16 of the largest coordinate magnitude of the apex or of ANY box of the scene -- hence never smaller
+// than the per-box tolerance above: the test culls a subset of what that one culls, and that one culls no box a ray of the
+// cone can touch.  (Its own rounding: a few ulp of the coordinate magnitude, 2^-23, against the 2^-16 of the tolerance.)
+struct ConePlanes {
+    V3 apex, axis, absAxis;
+    V3 n0, n1, n2, n3, a0, a1, a2, a3;      // face normals and their absolute values
+    float tol;
+};
+// (bmin, bmax) may arrive as (near, far) per axis -- the octant copies of the nodes store them that way: the centre is
+// symmetric in the two and the half extent is taken as |far - centre|, so no swap back is needed.)
+__device__ __forceinline__ bool coneMayTouchBoxCH(const ConePlanes& P, const V3 bmin, const V3 bmax, float& key)
+{
+    const V3 mid = vmuls(vadd(bmin, bmax), 0.5f);
+    const V3 c = vsub(mid, P.apex), d = vsub(bmax, mid), h = mk(fabsf(d.x), fabsf(d.y), fabsf(d.z));
+    key = vdot(P.axis, c);                              // (the same expression as the sort key of the first form)
+    const float m0 = fdot(P.n0, c) - fdot(P.a0, h), m1 = fdot(P.n1, c) - fdot(P.a1, h);
+    const float m2 = fdot(P.n2, c) - fdot(P.a2, h), m3 = fdot(P.n3, c) - fdot(P.a3, h);
+    const float M = key + fdot(P.absAxis, h);
+    // (NaN compares false: never culls)
+    return !(m0 > P.tol) && !(m1 > P.tol) && !(m2 > P.tol) && !(m3 > P.tol) && !(M < -P.tol);
 }
 
 // Child boxes of a node read from the copy of direction octant (sx, sy, sz): that copy stores (near, far) per axis, i.e.
@@ -765,6 +793,7 @@ __device__ __forceinline__ void entryAppend(EntryList& L, int ref, float key, bo
 __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, const EyeParams ep, int4* __restrict__ entries,
                                                       int* __restrict__ lists)
 {
+    asm volatile("griddepcontrol.launch_dependents;");      // the trace kernel may move in; it waits before it reads the entries
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long idx = tid / kEntryK;
     const int lane = (int)(tid % kEntryK);
@@ -805,6 +834,71 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     const float4* __restrict__ coneNodes = sc.nodes + (size_t)((csx ? 1 : 0) | (csy ? 2 : 0) | (csz ? 4 : 0)) * sc.nodeVariantStride;
 
     EntryList L;
+#if CR_ENTRY_V2
+    // Second form of the descent (same replacement rules, about 250 instead of 390 instructions per level -- the pass is a
+    // chain of dependent instructions of ~1.7 warps per scheduler, so its time is its instruction count): each lane keeps only
+    // ITS slot (ref, key, final); the group's flags travel as ballots, every lane replays the four replacement decisions on
+    // those bit fields to learn which (old slot, child) lands in its slot, and pulls that entry with shuffles.
+    ConePlanes CP;
+    CP.apex = C.apex; CP.axis = C.axis; CP.absAxis = mk(fabsf(C.axis.x), fabsf(C.axis.y), fabsf(C.axis.z));
+    CP.n0 = C.n0; CP.n1 = C.n1; CP.n2 = C.n2; CP.n3 = C.n3;
+    CP.a0 = mk(fabsf(C.n0.x), fabsf(C.n0.y), fabsf(C.n0.z)); CP.a1 = mk(fabsf(C.n1.x), fabsf(C.n1.y), fabsf(C.n1.z));
+    CP.a2 = mk(fabsf(C.n2.x), fabsf(C.n2.y), fabsf(C.n2.z)); CP.a3 = mk(fabsf(C.n3.x), fabsf(C.n3.y), fabsf(C.n3.z));
+    CP.tol = fmaxf(fmaxf(fmaxf(fabsf(C.apex.x), fabsf(C.apex.y)), fabsf(C.apex.z)), sc.boundsAbsMax) * 1.52587890625e-05f;
+    const int gbase = (int)(threadIdx.x & 31u) & ~(kEntryK - 1);       // first lane of my group within the warp
+    int myRef = lane == 0 ? 0 : kSentinel, nList = 1;
+    float myKey = 0.0f;
+    bool myFin = !ok;                                                  // not ok: the root stays the only entry
+    for (int iter = 0; iter < ep.entryMaxLevels; iter++) {             // (stopping early leaves a coarser but equally valid frontier)
+        const bool active = lane < nList && !myFin;
+        const unsigned bAct = __ballot_sync(0xffffffffu, active);
+        if (bAct == 0u) break;                                         // warp-uniform exit
+        int r0 = kSentinel, r1 = kSentinel;
+        float k0 = 0.0f, k1 = 0.0f;
+        bool h0 = false, h1 = false, stop = false;
+        if (active) {
+            const float4* np = coneNodes + 4 * (size_t)myRef;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            r0 = __float_as_int(n3.x); r1 = __float_as_int(n3.y);
+            // (near, far) planes as stored in the cone axis's octant copy: see coneMayTouchBoxCH
+            h0 = coneMayTouchBoxCH(CP, mk(n0.x, n0.z, n2.x), mk(n0.y, n0.w, n2.y), k0);
+            h1 = coneMayTouchBoxCH(CP, mk(n1.x, n1.z, n2.z), mk(n1.y, n1.w, n2.w), k1);
+            stop = (h0 && r0 < 0) || (h1 && r1 < 0);                   // never hand out leaves: their triangles would be tested without the per-ray box test
+        }
+        const unsigned gAct = (bAct >> gbase) & 15u;
+        const unsigned gH0 = (__ballot_sync(0xffffffffu, h0) >> gbase) & 15u, gH1 = (__ballot_sync(0xffffffffu, h1) >> gbase) & 15u;
+        const unsigned gStop = (__ballot_sync(0xffffffffu, stop) >> gbase) & 15u, gFin = (__ballot_sync(0xffffffffu, myFin) >> gbase) & 15u;
+        int cnt = 0, src = 0, kind = -1;                               // my new entry: old slot src; kind 0 = that entry itself, 1 / 2 = its child 0 / 1
+        bool newFin = false;
+#pragma unroll
+        for (int i = 0; i < kEntryK; i++) {
+            if (i < nList) {
+                const bool a = (gAct >> i) & 1u, c0 = (gH0 >> i) & 1u, c1 = (gH1 >> i) & 1u;
+                const bool keep = !a || ((gStop >> i) & 1u) || cnt + (int)c0 + (int)c1 + (nList - 1 - i) > kEntryBudget;
+                if (keep) {
+                    if (cnt == lane) { src = i; kind = 0; newFin = a || ((gFin >> i) & 1u); }
+                    cnt++;
+                } else {
+                    if (c0) { if (cnt == lane) { src = i; kind = 1; newFin = false; } cnt++; }
+                    if (c1) { if (cnt == lane) { src = i; kind = 2; newFin = false; } cnt++; }
+                }
+            }
+        }
+        const int sl = gbase + src;
+        const int pRef = __shfl_sync(0xffffffffu, myRef, sl), pR0 = __shfl_sync(0xffffffffu, r0, sl), pR1 = __shfl_sync(0xffffffffu, r1, sl);
+        const float pKey = __shfl_sync(0xffffffffu, myKey, sl), pK0 = __shfl_sync(0xffffffffu, k0, sl), pK1 = __shfl_sync(0xffffffffu, k1, sl);
+        myRef = kind < 0 ? kSentinel : (kind == 0 ? pRef : (kind == 1 ? pR0 : pR1));
+        myKey = kind < 0 ? 0.0f : (kind == 0 ? pKey : (kind == 1 ? pK0 : pK1));
+        myFin = newFin;
+        nList = cnt;
+    }
+#pragma unroll
+    for (int k = 0; k < kEntryK; k++) {
+        L.ref[k] = __shfl_sync(0xffffffffu, myRef, gbase + k);
+        L.key[k] = __shfl_sync(0xffffffffu, myKey, gbase + k);
+    }
+    L.n = nList; L.fin = 0u;
+#else
 #pragma unroll
     for (int k = 0; k < kEntryK; k++) { L.ref[k] = kSentinel; L.key[k] = 0.0f; }
     L.ref[0] = 0;
@@ -860,6 +954,7 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
         }
         L = Nw;
     }
+#endif
     // near to far along the axis (kEntryK = 4: fixed compare-exchange network, empty slots last); every lane of the
     // group holds the same list and sorts it the same way
 #pragma unroll
@@ -992,6 +1087,7 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
     // that holds the last real ticket of a slot keeps drawing until the slot's sequence runs into a block beyond the end.
     // Tickets per slot <= units + 2 per warp, hence j < units/32 + gridWarps/16 + 2 <= smCap (sized by the host).
     const bool smMode = ep.smSeq != nullptr;                               // (uniform)
+    asm volatile("griddepcontrol.launch_dependents;");                    // (the reduction kernel waits for this grid's completion itself)
     // (the slot is read once: re-reading %smid per ticket measured slower -- 23.4 vs 24.3 Grays/s batched -- and a first version
     //  that derived it with two integer modulos per unit spent 5 % of the per-frame kernel's instructions on them)
     unsigned mySlot = 0u;
@@ -1027,6 +1123,8 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
         chunk = __shfl_sync(kFullMask, t0, 0);
         nextChunk = t1;
     }
+    // Programmatic dependent launch: everything above ran beside the frontier pass; its entries are read from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (;;) {                                                             // (every branch on chunk / nextChunk is warp-uniform)
       if (smMode) {
           unsigned u = 0u;
@@ -1339,6 +1437,7 @@ __global__ void __launch_bounds__(32 * kSumPartialWarps) k_sumPartials(const flo
                                                                        uchar4* __restrict__ fastRowHost)
 {
     __shared__ uchar4 sPx[32 * kSumPartialWarps];
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (programmatic dependent launch: the partials of the trace kernel)
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
     const int rowsPerWarp = 32 / lanesPerRow, rowsPerCta = rowsPerWarp * kSumPartialWarps;
     const int row0 = (int)blockIdx.x * rowsPerCta;
@@ -1750,9 +1849,33 @@ void launchPrepOmmatidia(const float4* omm, int N, float4* pre, cudaStream_t str
     k_prepOmmatidia<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(omm, N, pre);
 }
 
+// Programmatic dependent launch (sm_90+): with the attribute, a kernel may be scheduled as soon as every CTA of the kernel
+// before it in the stream has executed griddepcontrol.launch_dependents (or exited); what it reads from that kernel it
+// reads behind its own griddepcontrol.wait, which returns when the earlier grid has completed and its writes are visible.
+// The frontier pass releases the trace kernel at once -- whose warps draw their first tickets and prefetch their first
+// states while the pass's latency chain runs -- and the trace kernel releases the reduction kernel, whose CTAs then move in as
+// the trace kernel's leave: two launch latencies off the frame.
+template <typename... KArgs, typename... Args>
+static void launchMaybePdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <bool FUSED, bool FAST>
 static void launchTraceT(const DeviceScene& sc, const EyeParams& eye, int grid, cudaStream_t stream)
 {
+    if (eye.pdl) {
+        if (eye.poses && eye.frameGroups > 1) launchMaybePdl(k_traceCompound<false, true, FUSED, FAST, true>, (unsigned)grid, kTraceThreads, stream, true, sc, eye);
+        else if (eye.poses) launchMaybePdl(k_traceCompound<false, true, FUSED, FAST, false>, (unsigned)grid, kTraceThreads, stream, true, sc, eye);
+        else launchMaybePdl(k_traceCompound<false, false, FUSED, FAST, false>, (unsigned)grid, kTraceThreads, stream, true, sc, eye);
+        return;
+    }
     if (eye.poses && eye.frameGroups > 1) k_traceCompound<false, true, FUSED, FAST, true><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else if (eye.poses) k_traceCompound<false, true, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
     else k_traceCompound<false, false, FUSED, FAST><<<grid, kTraceThreads, 0, stream>>>(sc, eye);
@@ -1767,8 +1890,8 @@ static void launchSumT(const EyeParams& eye, cudaStream_t stream)
         int lanesPerRow = 1;
         while (lanesPerRow < bpr && lanesPerRow < 32) lanesPerRow <<= 1;
         const long long rowsPerCta = (32 / lanesPerRow) * (long long)kSumPartialWarps;
-        k_sumPartials<FAST><<<(unsigned)((nf + rowsPerCta - 1) / rowsPerCta), 32 * kSumPartialWarps, 0, stream>>>(
-            eye.partials, (int)nf, bpr, lanesPerRow, eye.summed, eye.fastRow, eye.fastRowCount, eye.fastRowHost);
+        launchMaybePdl(k_sumPartials<FAST>, (unsigned)((nf + rowsPerCta - 1) / rowsPerCta), 32u * kSumPartialWarps, stream, eye.pdl && eye.queueRays == nullptr,
+                       (const float4*)eye.partials, (int)nf, bpr, lanesPerRow, eye.summed, eye.fastRow, eye.fastRowCount, eye.fastRowHost);
         return;
     }
     static const bool useTma = [] { const char* e = getenv("CR_SUM_TMA"); return e ? atoi(e) != 0 : true; }();

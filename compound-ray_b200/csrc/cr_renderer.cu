@@ -67,6 +67,7 @@ Renderer::Renderer()
     if (const char* e = getenv("CR_DYNAMIC_CHUNKS")) dynamicChunks = atoi(e) != 0;
     if (const char* e = getenv("CR_CHUNK_UNITS")) chunkUnits = atoi(e);
     if (const char* e = getenv("CR_SM_AFFINE")) smAffine = atoi(e);
+    if (const char* e = getenv("CR_PDL")) pdl = atoi(e) != 0;
     if (const char* e = getenv("CR_SM_AFFINE_MIN_BLOCKS")) smAffineMinBlocks = atoi(e);
     if (const char* e = getenv("CR_ENTRY_MAX_LEVELS")) entryMaxLevels = atoi(e);
     if (const char* e = getenv("CR_STANDING_FRONTIER")) standingFrontier = atoi(e) != 0;
@@ -298,6 +299,9 @@ void Renderer::uploadScene()
     dscene_.nodeVariantStride = static_cast<size_t>(4) * static_cast<size_t>(bvh_.nNodes);
     dscene_.nTris = bvh_.nTris;
     dscene_.missShader = scene_.missShader;
+    float absMax = 0.0f;
+    for (int a = 0; a < 3; a++) absMax = fmaxf(absMax, fmaxf(fabsf(smin[a]), fabsf(smax[a])));
+    dscene_.boundsAbsMax = absMax * 1.001f;            // (leaf boxes are padded by 2^-20 relative: well inside)
     if (verbose)
         std::cout << "[PyEye] scene on device: " << T << " triangles, " << bvh_.nNodes << " BVH nodes, built in "
                   << bvh_.buildMs << " ms" << std::endl;
@@ -630,6 +634,7 @@ void Renderer::launchCompound(CompoundState& cs, const HostCamera& cam, const Po
     EyeParams ep;
     ep.fastRowHost = fastRowHost;
     ep.fast = fastMath;
+    ep.pdl = pdl && !profileFrame;
     ep.nodeLanes = std::max(1, std::min(32, nodeLanes));
     ep.entryMaxLevels = std::max(1, entryMaxLevels);
     if (fusedActive(cs, cam)) {
@@ -678,6 +683,7 @@ void Renderer::launchCompoundBatch(CompoundState& cs, const DevicePose* dPoses, 
 {
     EyeParams ep;
     ep.fast = fastMath;
+    ep.pdl = pdl && !profileFrame;
     ep.nodeLanes = std::max(1, std::min(32, nodeLanes));
     ep.entryMaxLevels = std::max(1, entryMaxLevels);
     if (dSamples == nullptr) {             // fused reduction: the caller sized cs.dPartials for nFrames

@@ -125,6 +125,7 @@ public:
     int entryMaxLevels = 256;          // frontier pass: levels it may descend (a latency chain: one dependent node fetch per level)
     int chunkUnits = 1;                // single-frame trace kernel: units of 32 rays per counter fetch (larger chunks of one ommatidium's
                                        // units measured slower: 2 -> 623, 4 -> 723, 8 -> 993 us per headline frame)
+    bool pdl = true;                   // programmatic dependent launch of the trace kernel behind the frontier pass and of the reduction behind the trace
     int smAffine = 1;                  // trace kernel: blocks of 32 units stay on one SM (per-SM tickets, EyeParams::smSeq); needs dynamicChunks
     int smAffineMinBlocks = 16;        // ... in launches of at least this many blocks per SM (a block is to an SM what a unit is to a warp)
     bool dynamicChunks = true;         // trace kernel: ray units handed out through a global counter instead of a static grid-stride split
