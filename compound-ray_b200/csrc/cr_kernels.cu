@@ -1124,6 +1124,8 @@ __global__ void __launch_bounds__(kTraceThreads, CR_TRACE_MIN_BLOCKS) k_traceCom
         nextChunk = t1;
     }
     // Programmatic dependent launch: everything above ran beside the frontier pass; its entries are read from here on.
+    // (waiting only before the first read of the entries -- a unit's state load and ray construction ahead of it -- measured the
+    //  same: 0.550 vs 0.551 ms per frame)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (;;) {                                                             // (every branch on chunk / nextChunk is warp-uniform)
       if (smMode) {

@@ -1027,23 +1027,27 @@ bool Renderer::launchReadAhead(CompoundState& cs, const HostCamera& cam)
     if (cs.standingFrames < cs.aheadStreakNeeded || cs.lastSingleFrameMs <= 0.0) return false;
     const bool fused = fusedActive(cs, cam);
     // batches start short and double while they are consumed to the end (cs.aheadFrames), up to the GPU-time budget
-    size_t F = static_cast<size_t>(std::min(64.0, readAheadBudgetMs / std::max(cs.lastSingleFrameMs, 1e-3)));
-    F = std::min<size_t>(F, static_cast<size_t>(cs.aheadFrames));
+    const size_t Fbudget = static_cast<size_t>(std::min(64.0, readAheadBudgetMs / std::max(cs.lastSingleFrameMs, 1e-3)));
+    size_t F = std::min<size_t>(Fbudget, static_cast<size_t>(cs.aheadFrames));
     F = std::min(F, batchFramesPerLaunch(cs, F, fused));
     if (F < 2) return false;
     const size_t N = static_cast<size_t>(cs.N);
-    ensureBatchBuffers(cs, F, fused);
-    if (cs.aheadRowCap < F * N) {
+    // Buffers for the longest batch the ramp can reach, not for this one: growing them at every doubling (4, 8, 16, 32, 64
+    // frames) put a round of cudaFree / cudaMalloc / cudaFreeHost / cudaMallocHost into frames 10, 26, 58, ... of every standing
+    // run -- 1 to 50 ms each on a quiet host, 0.9 s seen on a busy one (benchmarks/speed_probe.py), against 13 us per frame.
+    const size_t Fcap = std::max(F, std::min(Fbudget, batchFramesPerLaunch(cs, Fbudget, fused)));
+    ensureBatchBuffers(cs, Fcap, fused);
+    if (cs.aheadRowCap < Fcap * N) {
         dfree(cs.dAheadRows);
         if (cs.hAheadRows) cudaFreeHost(cs.hAheadRows);
-        cs.dAheadRows = dallocT<uchar4>(F * N);
-        CR_CUDA(cudaMallocHost(&cs.hAheadRows, sizeof(uchar4) * F * N));
-        cs.aheadRowCap = F * N;
+        cs.dAheadRows = dallocT<uchar4>(Fcap * N);
+        CR_CUDA(cudaMallocHost(&cs.hAheadRows, sizeof(uchar4) * Fcap * N));
+        cs.aheadRowCap = Fcap * N;
     }
-    if (cs.batchPoseCap < F) {
+    if (cs.batchPoseCap < Fcap) {
         dfree(cs.dBatchPoses);
-        cs.dBatchPoses = dallocT<DevicePose>(F);
-        cs.batchPoseCap = F;
+        cs.dBatchPoses = dallocT<DevicePose>(Fcap);
+        cs.batchPoseCap = Fcap;
     }
     const DevicePose dp = toDevicePose(cam.pose);
     std::vector<DevicePose> hPoses(F, dp);

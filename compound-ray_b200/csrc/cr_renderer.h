@@ -127,7 +127,8 @@ public:
                                        // units measured slower: 2 -> 623, 4 -> 723, 8 -> 993 us per headline frame)
     bool pdl = true;                   // programmatic dependent launch of the trace kernel behind the frontier pass and of the reduction behind the trace
     int smAffine = 1;                  // trace kernel: blocks of 32 units stay on one SM (per-SM tickets, EyeParams::smSeq); needs dynamicChunks
-    int smAffineMinBlocks = 16;        // ... in launches of at least this many blocks per SM (a block is to an SM what a unit is to a warp)
+    int smAffineMinBlocks = 48;        // ... in launches of at least this many blocks per SM: an SM that holds a heavy block runs 32 latency-bound warps at once,
+                                       // so the tail of a launch is longer than with mixed units (21 blocks per SM: 0.187 vs 0.148 ms per frame of 1000 x 3200)
     bool dynamicChunks = true;         // trace kernel: ray units handed out through a global counter instead of a static grid-stride split
     int wavefront = 0;
     int nodeLanes = 16;                // phase switch of the per-lane BVH walk (EyeParams::nodeLanes); 1 = classic while-while

@@ -241,7 +241,7 @@ void crDebugFrameBreakdown(float* out3);
 void crDebugSetDynamicChunks(int on);
 /* ... and, on top of the counter, SM-affine hand-out: blocks of 32 consecutive units stay on ONE SM, whose warps share them
  * through a per-SM ticket counter (at S = 1024 an SM's 32 resident warps trace one ommatidium together: its nodes are fetched
- * into that SM's L1 once).  on = 1 (default), in launches of at least minBlocksPerSm (default 16) blocks per SM.  Result-neutral. */
+ * into that SM's L1 once).  on = 1 (default), in launches of at least minBlocksPerSm (default 48) blocks per SM.  Result-neutral. */
 void crDebugSetSmAffine(int on, int minBlocksPerSm);
 /* single_dimension_fast rows written by the reduction kernel straight into the pinned (mapped) host frame when the caller
  * reads every frame: 1 (default) on, 0 = always a device-to-host copy behind the frame's kernels.  Same bytes. */

@@ -37,7 +37,7 @@ def _default_modes(lib):
     lib.crDebugSetWavefront(0, 24, 0.35)
     lib.crDebugSetNodeLanes(16)
     lib.crDebugSetDynamicChunks(1)
-    lib.crDebugSetSmAffine(1, 16)
+    lib.crDebugSetSmAffine(1, 48)
     lib.crDebugSetZeroCopy(1)
     lib.crDebugSetReadAhead(1, 1.5)
     lib.crDebugSetFrameGroups(1)
@@ -255,8 +255,8 @@ def test_sm_affine_hand_out_changes_no_bit(lib, er, loader, oracle, terrain):
         want_fused = oracle.fused_sum(eye.last["compound"], N, S) if S % 32 == 0 else None
         out = {}
         for fused in (0, 1):
-            for key, (on, minb, zc) in {"off": (0, 16, 1), "default": (1, 16, 1), "forced": (1, 0, 1), "two": (1, 2, 1),
-                                        "copy": (1, 16, 0)}.items():
+            for key, (on, minb, zc) in {"off": (0, 48, 1), "default": (1, 48, 1), "forced": (1, 0, 1), "two": (1, 2, 1),
+                                        "copy": (1, 2, 0)}.items():
                 lib.crSetRenderMode(fused, 0)
                 lib.crDebugSetZeroCopy(zc)            # 8-bit row straight into the mapped host frame / device-to-host copy
                 lib.crDebugSetSmAffine(on, minb)
