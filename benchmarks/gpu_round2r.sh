@@ -2,7 +2,7 @@
 # Evidence refresh for the final round-2 tree: all GPU tests, ncu captures for profiles/k1_traffic.json, full ncu of the batched and
 # per-frame trace kernels, bench lines, launch list, configs, speed-test protocol.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-T=${TAG:-r04e}
+T=${TAG:-r04n}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu --durations=8 > gpurun_out/${T}_gpu_tests.log 2>&1; echo "all gpu tests rc=$?"
 tail -14 gpurun_out/${T}_gpu_tests.log | cut -c1-160

@@ -14,6 +14,8 @@ PAT = {"LDG.E.*256 (256-bit node loads, new with sm_100)": r"LDG\.E\S*\.256", "F
        "UBLKCP (bulk TMA copy)": r"UBLKCP", "SYNCS (mbarrier)": r"SYNCS", "SHFL.BFLY (fused reduction butterfly)": r"SHFL\.BFLY",
        "MUFU (hardware sin/cos/lg2/ex2/rcp/rsq)": r"MUFU\.", "VOTE / ballot": r"VOTE", "WARPSYNC": r"WARPSYNC", "LDS": r"\bLDS", "STS": r"\bSTS",
        "LDL (local-memory stack spill levels)": r"\bLDL", "STL": r"\bSTL", "FFMA": r"FFMA",
+       "ACQBULK (griddepcontrol.wait: programmatic dependent launch)": r"ACQBULK", "PREEXIT (griddepcontrol.launch_dependents)": r"PREEXIT",
+       "S2R SR_VIRTUALSMID (%smid: SM-affine hand-out)": r"SR_VIRTUALSMID", "ATOMG (work counter, per-SM tickets)": r"ATOMG",
        "HMMA/tensor ops (none expected: no contraction on this path)": r"HMMA|UTCHMMA|TCGEN|QGMMA"}
 WANT = ["k_traceCompound", "k_sumSamplesTma", "k_sumPartials", "k_buildEntries", "k_camera"]
 
