@@ -868,21 +868,22 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
         const unsigned gAct = (bAct >> gbase) & 15u;
         const unsigned gH0 = (__ballot_sync(0xffffffffu, h0) >> gbase) & 15u, gH1 = (__ballot_sync(0xffffffffu, h1) >> gbase) & 15u;
         const unsigned gStop = (__ballot_sync(0xffffffffu, stop) >> gbase) & 15u, gFin = (__ballot_sync(0xffffffffu, myFin) >> gbase) & 15u;
+        // (branch-free: the groups of a warp take different paths, so branches here would run every path for everybody)
         int cnt = 0, src = 0, kind = -1;                               // my new entry: old slot src; kind 0 = that entry itself, 1 / 2 = its child 0 / 1
         bool newFin = false;
 #pragma unroll
         for (int i = 0; i < kEntryK; i++) {
-            if (i < nList) {
-                const bool a = (gAct >> i) & 1u, c0 = (gH0 >> i) & 1u, c1 = (gH1 >> i) & 1u;
-                const bool keep = !a || ((gStop >> i) & 1u) || cnt + (int)c0 + (int)c1 + (nList - 1 - i) > kEntryBudget;
-                if (keep) {
-                    if (cnt == lane) { src = i; kind = 0; newFin = a || ((gFin >> i) & 1u); }
-                    cnt++;
-                } else {
-                    if (c0) { if (cnt == lane) { src = i; kind = 1; newFin = false; } cnt++; }
-                    if (c1) { if (cnt == lane) { src = i; kind = 2; newFin = false; } cnt++; }
-                }
-            }
+            const int inList = i < nList ? 1 : 0;
+            const int a = (int)((gAct >> i) & 1u), c0 = (int)((gH0 >> i) & 1u), c1 = (int)((gH1 >> i) & 1u);
+            const int keep = (a ^ 1) | (int)((gStop >> i) & 1u) | (cnt + c0 + c1 + (nList - 1 - i) > kEntryBudget ? 1 : 0);
+            const int nOut = inList * (keep ? 1 : c0 + c1);
+            const int pos = lane - cnt;
+            const bool mine = pos >= 0 && pos < nOut;
+            const int kindHere = keep ? 0 : ((pos == 0 && c0) ? 1 : 2);
+            src = mine ? i : src;
+            kind = mine ? kindHere : kind;
+            newFin = mine ? (keep && (a || ((gFin >> i) & 1u))) : newFin;
+            cnt += nOut;
         }
         const int sl = gbase + src;
         const int pRef = __shfl_sync(0xffffffffu, myRef, sl), pR0 = __shfl_sync(0xffffffffu, r0, sl), pR1 = __shfl_sync(0xffffffffu, r1, sl);
