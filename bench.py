@@ -95,7 +95,30 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device = device
+        # nvidia-smi numbers the PHYSICAL GPUs; the CUDA ordinal is an index into CUDA_VISIBLE_DEVICES when that is set
+        # (sampling GPU 0 while the work runs on another one reads an idle clock).  Prefer the UUID torch reports.
+        self.device = str(device)
+        uuid = None
+        try:
+            import torch
+            uuid = getattr(torch.cuda.get_device_properties(int(device)), "uuid", None)
+        except Exception:
+            uuid = None
+        if uuid is not None:
+            u = str(uuid)
+            self.device = u if u.startswith("GPU-") else "GPU-" + u
+        else:
+            ids = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+            if ids and int(device) < len(ids):
+                self.device = ids[int(device)]
+        if self.device != str(device):                  # make sure nvidia-smi accepts that name, else the plain ordinal
+            try:
+                ok = subprocess.run(["nvidia-smi", "-i", self.device, "--query-gpu=index", "--format=csv,noheader"],
+                                    capture_output=True, text=True, timeout=10).returncode == 0
+            except Exception:
+                ok = False
+            if not ok:
+                self.device = str(device)
         self.lines = []
         self.proc = None
 
