@@ -11,6 +11,31 @@ if not os.path.exists(os.path.join(data, "data", "test-scene", "test-scene.gltf"
     with tarfile.open(os.path.join(_ROOT, "tests", "golden", "reference_data.tar.gz")) as tar:
         tar.extractall(data, filter="data")
 lib = er.load_library(device=0); lib.setVerbosity(False)
+if os.environ.get("CR_SANITIZE_SECTION", "") == "affine":
+    # last session's paths only: SM-affine hand-out forced on for launches of any size (per-SM tickets, epoch-tagged block table,
+    # ragged last blocks, grouped and ungrouped batches, consecutive launches), the second form of the frontier pass, programmatic
+    # dependent launch of trace and reduction kernels, read-ahead buffers sized for the ramp's longest batch
+    lib.loadGlTFscene(os.path.join(data, "data/natural-standin-sky.gltf").encode())
+    er.gotoFirstCompoundEye(lib)
+    N = lib.getCurrentEyeOmmatidialCount()
+    lib.setCurrentEyeShaderName(b"single_dimension_fast"); er.setRenderSize(lib, N, 1)
+    lib.crDebugSetEntryFrontier(1, 2, 0)
+    for on, minb in ((1, 0), (1, 2), (0, 48)):
+        lib.crDebugSetSmAffine(on, minb)
+        for fused in (1, 0):
+            lib.crSetRenderMode(fused, 0)
+            for S in (32, 40, 96, 7):
+                lib.setCurrentEyeSamplesPerOmmatidium(S)
+                for k in range(3):
+                    lib.setCameraPosition(0.1 * k, 0.2, 0.05 * k); lib.renderFrame(); lib.getFramePointer()
+                for k in range(12):
+                    lib.renderFrame(); lib.getFramePointer()
+                lib.setCameraPosition(0.3, 0.1, 0.0); lib.renderFrame(); lib.getFramePointer()
+                for n in (9, 6):
+                    er.renderPoseBatch(lib, er.make_poses(np.random.default_rng(n).uniform(-1, 1, (n, 3))))
+    lib.stop()
+    print("sanitize tour (affine section) done")
+    sys.exit(0)
 for scene, cam in (("data/test-scene/test-scene.gltf", b"insect-cam-2"), ("data/natural-standin-sky.gltf", None)):
     lib.loadGlTFscene(os.path.join(data, scene).encode())
     if cam: assert lib.gotoCameraByName(cam)
