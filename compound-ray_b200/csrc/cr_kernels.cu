@@ -827,7 +827,8 @@ __global__ void __launch_bounds__(128) k_buildEntries(const DeviceScene sc, cons
     C.n3 = vadd(vmuls(v, -ch), back);
 
     // The pass reads the node copy of the CONE AXIS's direction octant -- the copy most of this ommatidium's sample rays will
-    // read in the trace kernel -- and swaps its (near, far) planes back to (min, max): what it fetches is then warm in L2 for
+    // read in the trace kernel (the first form swaps its (near, far) planes back to (min, max), the second form's test is
+    // symmetric in them): what it fetches is then warm in L2 for
     // the rays (and, while the camera moves slowly, already warm from the previous frame's rays), instead of living in copy 0
     // that no ray of this cone touches.
     const bool csx = C.axis.x < 0.0f, csy = C.axis.y < 0.0f, csz = C.axis.z < 0.0f;
